@@ -1,0 +1,203 @@
+/* pcc_attr_b200.h — C ABI of the B200-native G-PCC attribute-transform path.
+ *
+ * Drop-in boundary for the attribute-transform hot path of MPEG G-PCC TMC13
+ * (release-23.0-rc2).  Every entry point is `extern "C"`, takes plain host
+ * pointers and sizes (no torch / C++ types) and returns an int status
+ * (PCCB200_OK == 0).  The functions are synchronous: results are in the
+ * caller's host buffers on return, mirroring the reference's own blocking
+ * calls.
+ *
+ * Reference interfaces replaced (paths relative to the TMC13 tree):
+ *   pccb200_raht_forward   <- pcc::regionAdaptiveHierarchicalTransform
+ *                             tmc3/RAHT.h:47-57, tmc3/RAHT.cpp:1997-2018
+ *   pccb200_raht_inverse   <- pcc::regionAdaptiveHierarchicalInverseTransform
+ *                             tmc3/RAHT.h:59-69, tmc3/RAHT.cpp:2037-2058
+ *   pccb200_morton_sort    <- mortonAddr + std::sort(MortonCodeWithIndex)
+ *                             tmc3/AttributeEncoder.cpp:1316-1321,
+ *                             tmc3/AttributeDecoder.cpp:623-628,
+ *                             tmc3/PCCMath.h:605-626
+ *   pccb200_attr_raht_encode / _decode
+ *                          <- the sort + gather + transform + clip body of
+ *                             AttributeEncoder::encode{Colors,Reflectances}TransformRaht
+ *                             tmc3/AttributeEncoder.cpp:1214-1375 and
+ *                             AttributeDecoder::decode{Colors,Reflectance}Raht
+ *                             tmc3/AttributeDecoder.cpp:527-674 (entropy
+ *                             coding stays on the host, in the caller)
+ *   pccb200_quant_weights  <- pcc::PCCComputeQuantizationWeights
+ *                             tmc3/PCCTMC3Common.h:828-854
+ *   pccb200_lift_forward / _inverse
+ *                          <- per-LoD PCCLiftPredict + PCCLiftUpdate loops
+ *                             tmc3/AttributeEncoder.cpp:1408-1415,1476-1482,
+ *                             tmc3/PCCTMC3Common.h:716-824
+ *
+ * Arithmetic is the reference's: Q.15 FixedPoint in int64 with
+ * round-half-away multiplies (tmc3/FixedPoint.h:113-122), the LUT+Newton
+ * isqrt/irsqrt (tmc3/misc.cpp:138-225) and the reciprocal-multiply Quantizer
+ * (tmc3/quantization.h:79-102).  Outputs are bit-identical to the reference.
+ */
+#ifndef PCC_ATTR_B200_H
+#define PCC_ATTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCCB200_ABI_VERSION 1
+
+/* status codes */
+#define PCCB200_OK 0
+#define PCCB200_ERR_INVALID_ARG 1   /* null pointer, bad size, A not in 1..3 */
+#define PCCB200_ERR_NO_DEVICE 2     /* no CUDA device / wrong architecture */
+#define PCCB200_ERR_CUDA 3          /* a CUDA runtime call failed */
+#define PCCB200_ERR_UNSORTED 4      /* morton[] not ascending */
+#define PCCB200_ERR_UNSUPPORTED 5   /* e.g. inter-frame prediction requested */
+#define PCCB200_ERR_NOMEM 6
+
+#define PCCB200_MAX_QP_LAYERS 32
+#define PCCB200_MAX_AC_QP_LAYERS 32
+
+/* Flattened pcc::RahtPredictionParams (tmc3/hls.h:439-466) plus the
+ * `rahtExtension` bool argument of the transform entry points. */
+typedef struct pccb200_raht_params {
+  int32_t prediction_enabled;         /* raht_prediction_enabled_flag */
+  int32_t integer_haar;               /* integer_haar_enable_flag */
+  int32_t prediction_threshold0;      /* raht_prediction_threshold0 */
+  int32_t prediction_threshold1;      /* raht_prediction_threshold1 */
+  int32_t subnode_prediction_enabled; /* raht_subnode_prediction_enabled_flag */
+  int32_t prediction_search_range;    /* raht_prediction_search_range */
+  int32_t pred_weight_parent[19];     /* predWeightParent */
+  int32_t pred_weight_child[12];      /* predWeightChild (used iff subnode) */
+  int32_t raht_extension;             /* aps.raht_extension */
+} pccb200_raht_params;
+
+/* Flattened pcc::QpSet (tmc3/quantization.h:123-137).  Region offsets reach
+ * the transform as per-point offsets (point_qp_offsets), exactly as in the
+ * reference (tmc3/AttributeEncoder.cpp:1337). */
+typedef struct pccb200_qpset {
+  int32_t num_layers;                                  /* layers.size() >= 1 */
+  int32_t layers[PCCB200_MAX_QP_LAYERS][2];            /* {luma, chroma offset} */
+  int32_t max_qp;
+  int32_t fixed_point_qp_offset;
+  int32_t num_ac_coeff_qp_layers;                      /* rahtAcCoeffQps.size() */
+  int32_t ac_coeff_qps[PCCB200_MAX_AC_QP_LAYERS][7][2];
+} pccb200_qpset;
+
+/* Fill p with the reference's defaults (tmc3/TMC3.cpp:1284-1318,
+ * tmc3/hls.h:451-465): prediction on, thresholds 2/6, sub-node prediction on
+ * with weights {9,3,1,5,2}, search range 50000, rahtExtension on. */
+void pccb200_raht_params_default(pccb200_raht_params* p);
+
+/* Derive the 19 + 12 prediction weights from the 5 signalled ones
+ * (RahtPredictionParams::setPredictionWeights, tmc3/hls.h:456-465). */
+void pccb200_raht_set_prediction_weights(pccb200_raht_params* p,
+                                         const int32_t w[5]);
+
+/* Library / device management ------------------------------------------- */
+
+int pccb200_abi_version(void);
+/* Selects the CUDA device used by this process' calls (default 0). */
+int pccb200_set_device(int device);
+/* Human-readable description of the last error on this thread. */
+const char* pccb200_last_error(void);
+/* Number of kernel launches issued by this library since process start. */
+uint64_t pccb200_kernel_launch_count(void);
+
+/* Morton sort ------------------------------------------------------------ */
+
+/* keys_out[i] = Morton code of the i-th point in ascending code order
+ * (x -> bit 2, y -> bit 1, z -> bit 0 of each triple), ties kept in input
+ * order; order_out[i] = its index in xyz.  xyz is N x 3 int32, coordinates in
+ * [0, 2^21). */
+int pccb200_morton_sort(const int32_t* xyz, int32_t n, int64_t* keys_out,
+                        int32_t* order_out);
+
+/* RAHT, reference-signature level ---------------------------------------- */
+
+/* morton: N ascending codes.  attrs_inout: N x A row-major int32; in: source
+ * values, out: reconstructed (unclipped) values.  coeffs_out: A x N planar.
+ * point_qp_offsets: N x 2 int32 or NULL for all-zero. */
+int pccb200_raht_forward(const pccb200_raht_params* params,
+                         const pccb200_qpset* qpset,
+                         const int32_t* point_qp_offsets,
+                         const int64_t* morton, int32_t* attrs_inout,
+                         int32_t num_attrs, int32_t n, int32_t* coeffs_out);
+
+/* coeffs_in: A x N planar quantised coefficients.  attrs_out: N x A. */
+int pccb200_raht_inverse(const pccb200_raht_params* params,
+                         const pccb200_qpset* qpset,
+                         const int32_t* point_qp_offsets,
+                         const int64_t* morton, int32_t* attrs_out,
+                         int32_t num_attrs, int32_t n,
+                         const int32_t* coeffs_in);
+
+/* RAHT, attribute-coder level (sort + gather + transform + clip on device) - */
+
+/* xyz: N x 3 positions in input (unsorted) order.  attrs_inout: N x A values
+ * in input order (uint16 range); on return the clipped reconstruction in
+ * input order, as AttributeEncoder writes back into the PCCPointSet3.
+ * coeffs_out: A x N planar, in coding order.  bitdepth gives the clip range
+ * [0, 2^bitdepth - 1].  point_qp_offsets: N x 2 in input order, or NULL. */
+int pccb200_attr_raht_encode(const pccb200_raht_params* params,
+                             const pccb200_qpset* qpset,
+                             const int32_t* point_qp_offsets,
+                             const int32_t* xyz, int32_t* attrs_inout,
+                             int32_t num_attrs, int32_t n, int32_t bitdepth,
+                             int32_t* coeffs_out);
+
+int pccb200_attr_raht_decode(const pccb200_raht_params* params,
+                             const pccb200_qpset* qpset,
+                             const int32_t* point_qp_offsets,
+                             const int32_t* xyz, int32_t* attrs_out,
+                             int32_t num_attrs, int32_t n, int32_t bitdepth,
+                             const int32_t* coeffs_in);
+
+/* Batched slices: the independent work units of a frame
+ * (tmc3/encoder.cpp:545-568).  Slice s owns points
+ * [slice_offsets[s], slice_offsets[s+1]) of every per-point array and the
+ * matching range of every planar coefficient component:
+ * coeffs[(k * total + slice_offsets[s]) ...] holds component k of slice s,
+ * i.e. each slice's coefficients are planar with stride `total`. */
+int pccb200_attr_raht_encode_slices(const pccb200_raht_params* params,
+                                    const pccb200_qpset* qpset,
+                                    const int32_t* point_qp_offsets,
+                                    const int32_t* xyz, int32_t* attrs_inout,
+                                    int32_t num_attrs, int32_t bitdepth,
+                                    const int64_t* slice_offsets,
+                                    int32_t num_slices, int32_t* coeffs_out);
+
+/* Lifting transform ------------------------------------------------------- */
+
+/* Flattened pcc::PCCPredictor as consumed by the lifting passes
+ * (tmc3/PCCTMC3Common.h:521-712): up to 3 neighbours, 8-bit fixed-point
+ * weights, neighbour given as predictor index. */
+typedef struct pccb200_predictor {
+  uint32_t neighbor_count;
+  uint32_t predictor_index[3];
+  uint32_t weight[3];
+} pccb200_predictor;
+
+/* qw_out[i] for i in [0, n): PCCComputeQuantizationWeights. */
+int pccb200_quant_weights(const pccb200_predictor* preds, int32_t n,
+                          const uint32_t* num_points_in_lod, int32_t lod_count,
+                          uint64_t* qw_out);
+
+/* attrs_inout: N x A int64 in predictor order (values already << 8).
+ * Forward: for lod = lod_count-1 .. 1: predict then update
+ * (tmc3/AttributeEncoder.cpp:1408-1415).  Inverse: lod = 1 .. lod_count-1:
+ * update then predict (tmc3/AttributeEncoder.cpp:1476-1482). */
+int pccb200_lift_forward(const pccb200_predictor* preds, const uint64_t* qw,
+                         int32_t n, const uint32_t* num_points_in_lod,
+                         int32_t lod_count, int64_t* attrs_inout,
+                         int32_t num_attrs);
+int pccb200_lift_inverse(const pccb200_predictor* preds, const uint64_t* qw,
+                         int32_t n, const uint32_t* num_points_in_lod,
+                         int32_t lod_count, int64_t* attrs_inout,
+                         int32_t num_attrs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCC_ATTR_B200_H */

@@ -1,0 +1,333 @@
+"""Shared test helpers: ctypes views of the C-ABI PODs, loaders for the
+oracle (oracle/liboracle.so) and the compiled reference
+(oracle/_ref/libtmc13_ref.so), and the synthetic point-cloud generators of
+SURVEY.md 8(d).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+MAX_QP_LAYERS = 32
+MAX_AC_QP_LAYERS = 32
+
+
+class RahtParams(C.Structure):
+    _fields_ = [
+        ("prediction_enabled", C.c_int32),
+        ("integer_haar", C.c_int32),
+        ("prediction_threshold0", C.c_int32),
+        ("prediction_threshold1", C.c_int32),
+        ("subnode_prediction_enabled", C.c_int32),
+        ("prediction_search_range", C.c_int32),
+        ("pred_weight_parent", C.c_int32 * 19),
+        ("pred_weight_child", C.c_int32 * 12),
+        ("raht_extension", C.c_int32),
+    ]
+
+
+class QpSet(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32),
+        ("layers", (C.c_int32 * 2) * MAX_QP_LAYERS),
+        ("max_qp", C.c_int32),
+        ("fixed_point_qp_offset", C.c_int32),
+        ("num_ac_coeff_qp_layers", C.c_int32),
+        ("ac_coeff_qps", ((C.c_int32 * 2) * 7) * MAX_AC_QP_LAYERS),
+    ]
+
+
+class Predictor(C.Structure):
+    _fields_ = [
+        ("neighbor_count", C.c_uint32),
+        ("predictor_index", C.c_uint32 * 3),
+        ("weight", C.c_uint32 * 3),
+    ]
+
+
+DEFAULT_PARENT_W = [4, 2, 2, 2, 1, 1, 1, 1, 1, 2, 1, 2, 2, 1, 1, 1, 1, 1, 1]
+
+
+def set_prediction_weights(p, w):
+    """RahtPredictionParams::setPredictionWeights (tmc3/hls.h:456-465)."""
+    child = [w[4], w[4], w[3], w[4], w[3], w[3], w[4], w[4], w[4], w[4], w[4], w[4]]
+    parent = [w[0], w[1], w[1], w[1], w[2], w[2], w[2], w[2], w[2], w[1], w[2],
+              w[1], w[1], w[2], w[2], w[2], w[2], w[2], w[2]]
+    for i in range(19):
+        p.pred_weight_parent[i] = parent[i]
+    for i in range(12):
+        p.pred_weight_child[i] = child[i]
+
+
+def make_params(prediction=1, haar=0, thr0=2, thr1=6, subnode=1,
+                search_range=50000, weights=(9, 3, 1, 5, 2), ext=1):
+    p = RahtParams()
+    p.prediction_enabled = prediction
+    p.integer_haar = haar
+    p.prediction_threshold0 = thr0
+    p.prediction_threshold1 = thr1
+    p.subnode_prediction_enabled = subnode
+    p.prediction_search_range = search_range
+    p.raht_extension = ext
+    for i in range(19):
+        p.pred_weight_parent[i] = DEFAULT_PARENT_W[i]
+    if subnode:
+        # TMC3.cpp:1894-1906: weights are only derived when sub-node
+        # prediction is on; otherwise the constructor defaults stay.
+        set_prediction_weights(p, list(weights))
+    return p
+
+
+def make_qpset(qp=34, chroma_offset=-2, bitdepth=8, layers=None,
+               fixed_point_qp_offset=0, ac_qps=None):
+    q = QpSet()
+    if layers is None:
+        layers = [(qp, chroma_offset)]
+    q.num_layers = len(layers)
+    for i, (a, b) in enumerate(layers):
+        q.layers[i][0] = a
+        q.layers[i][1] = b
+    q.max_qp = 51 + 6 * (bitdepth - 8)
+    q.fixed_point_qp_offset = fixed_point_qp_offset
+    q.num_ac_coeff_qp_layers = 0
+    if ac_qps is not None:
+        q.num_ac_coeff_qp_layers = len(ac_qps)
+        for l, layer in enumerate(ac_qps):
+            for c in range(7):
+                q.ac_coeff_qps[l][c][0] = layer[c][0]
+                q.ac_coeff_qps[l][c][1] = layer[c][1]
+    return q
+
+
+# --------------------------------------------------------------------------
+# library loaders
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+_oracle = None
+_ref = None
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+def load_oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path) or any(
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(path)
+            for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.oracle_raht.restype = C.c_int
+        lib.oracle_isqrt.restype = C.c_uint32
+        lib.oracle_isqrt.argtypes = [C.c_uint64]
+        lib.oracle_irsqrt.restype = C.c_uint64
+        lib.oracle_irsqrt.argtypes = [C.c_uint64]
+        lib.oracle_morton_addr.restype = C.c_int64
+        lib.oracle_morton_addr.argtypes = [C.c_int32] * 3
+        lib.oracle_morton3d_add.restype = C.c_uint64
+        lib.oracle_morton3d_add.argtypes = [C.c_uint64] * 2
+        lib.oracle_quantize.restype = C.c_int64
+        lib.oracle_quantize.argtypes = [C.c_int, C.c_int64]
+        lib.oracle_scale.restype = C.c_int64
+        lib.oracle_scale.argtypes = [C.c_int, C.c_int64]
+        lib.oracle_fixed_mul.restype = C.c_int64
+        lib.oracle_fixed_mul.argtypes = [C.c_int64] * 2
+        lib.oracle_div_approx.restype = C.c_int64
+        lib.oracle_div_approx.argtypes = [C.c_int64, C.c_uint64, C.c_int32]
+        _oracle = lib
+    return _oracle
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtmc13_ref.so"))
+
+
+def load_ref():
+    """The compiled, unmodified reference (built by `make -C oracle ref`)."""
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtmc13_ref.so"))
+        for name in ("tmc13ref_raht", "tmc13ref_morton_sort", "tmc13ref_attr_raht",
+                     "tmc13ref_quant_weights", "tmc13ref_lift"):
+            getattr(lib, name).restype = C.c_double
+        lib.tmc13ref_isqrt.restype = C.c_uint32
+        lib.tmc13ref_isqrt.argtypes = [C.c_uint64]
+        lib.tmc13ref_irsqrt.restype = C.c_uint64
+        lib.tmc13ref_irsqrt.argtypes = [C.c_uint64]
+        lib.tmc13ref_morton_addr.restype = C.c_int64
+        lib.tmc13ref_morton_addr.argtypes = [C.c_int32] * 3
+        lib.tmc13ref_morton3d_add.restype = C.c_uint64
+        lib.tmc13ref_morton3d_add.argtypes = [C.c_uint64] * 2
+        lib.tmc13ref_quantize.restype = C.c_int64
+        lib.tmc13ref_quantize.argtypes = [C.c_int, C.c_int64]
+        lib.tmc13ref_scale.restype = C.c_int64
+        lib.tmc13ref_scale.argtypes = [C.c_int, C.c_int64]
+        lib.tmc13ref_fixed_mul.restype = C.c_int64
+        lib.tmc13ref_fixed_mul.argtypes = [C.c_int64] * 2
+        lib.tmc13ref_div_approx.restype = C.c_int64
+        lib.tmc13ref_div_approx.argtypes = [C.c_int64, C.c_uint64, C.c_int32]
+        _ref = lib
+    return _ref
+
+
+def _run_raht(fn, forward, params, qpset, morton, attrs, coeffs, qpoffs):
+    n, a = attrs.shape
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    morton = np.ascontiguousarray(morton, dtype=np.int64)
+    if forward:
+        coeffs = np.zeros((a, n), dtype=np.int32)
+    else:
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.int32).copy()
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    r = fn(C.c_int(1 if forward else 0), C.byref(params), C.byref(qpset),
+           _ptr(qpoffs, C.c_int32), _ptr(morton, C.c_int64),
+           _ptr(attrs, C.c_int32), C.c_int(a), C.c_int(n),
+           _ptr(coeffs, C.c_int32))
+    return attrs, coeffs, r
+
+
+def oracle_raht(forward, params, qpset, morton, attrs, coeffs=None, qpoffs=None):
+    """-> (attrs_out [N,A], coeffs [A,N])"""
+    a, c, r = _run_raht(load_oracle().oracle_raht, forward, params, qpset,
+                        morton, attrs, coeffs, qpoffs)
+    assert r == 0
+    return a, c
+
+
+def ref_raht(forward, params, qpset, morton, attrs, coeffs=None, qpoffs=None,
+             want_time=False):
+    a, c, t = _run_raht(load_ref().tmc13ref_raht, forward, params, qpset,
+                        morton, attrs, coeffs, qpoffs)
+    return (a, c, t) if want_time else (a, c)
+
+
+def oracle_morton_sort(xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    n = xyz.shape[0]
+    keys = np.zeros(n, dtype=np.int64)
+    order = np.zeros(n, dtype=np.int32)
+    load_oracle().oracle_morton_sort(_ptr(xyz, C.c_int32), C.c_int(n),
+                                     _ptr(keys, C.c_int64), _ptr(order, C.c_int32))
+    return keys, order
+
+
+def ref_morton_sort(xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    n = xyz.shape[0]
+    keys = np.zeros(n, dtype=np.int64)
+    order = np.zeros(n, dtype=np.int32)
+    load_ref().tmc13ref_morton_sort(_ptr(xyz, C.c_int32), C.c_int(n),
+                                    _ptr(keys, C.c_int64), _ptr(order, C.c_int32))
+    return keys, order
+
+
+def np_morton(xyz):
+    """Vectorised Morton code (x->bit2, y->bit1, z->bit0), 21 bits/axis."""
+    xyz = np.asarray(xyz, dtype=np.int64)
+    out = np.zeros(xyz.shape[0], dtype=np.int64)
+    for b in range(21):
+        out |= ((xyz[:, 0] >> b) & 1) << (3 * b + 2)
+        out |= ((xyz[:, 1] >> b) & 1) << (3 * b + 1)
+        out |= ((xyz[:, 2] >> b) & 1) << (3 * b)
+    return out
+
+
+def sort_cloud(xyz, attrs):
+    """Stable Morton sort of a cloud; returns (morton, attrs_sorted, order)."""
+    keys = np_morton(xyz)
+    order = np.argsort(keys, kind="stable")
+    return keys[order], np.ascontiguousarray(attrs[order]), order
+
+
+# --------------------------------------------------------------------------
+# synthetic clouds
+
+def _smooth_attr(xyz, rng, a, noise=8, bitdepth=8):
+    x = xyz.astype(np.float64)
+    span = max(1.0, float(x.max()))
+    base = np.stack([
+        128 + 90 * np.sin(6.0 * x[:, 0] / span + 0.3) * np.cos(4.0 * x[:, 1] / span),
+        128 + 80 * np.cos(5.0 * x[:, 1] / span + 1.1) * np.sin(3.0 * x[:, 2] / span),
+        128 + 70 * np.sin(7.0 * (x[:, 0] + x[:, 2]) / span),
+    ], axis=1)[:, :a]
+    v = base * ((1 << bitdepth) / 256.0) + rng.integers(-noise, noise + 1, size=(xyz.shape[0], a))
+    return np.clip(np.rint(v), 0, (1 << bitdepth) - 1).astype(np.int32)
+
+
+def cloud_cube(n=100000, side=47, offset=8, seed=1, a=3):
+    """Config 1: first n voxels (Morton order) of a filled side^3 cube."""
+    rng = np.random.default_rng(seed)
+    g = np.arange(side, dtype=np.int32) + offset
+    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    keys = np_morton(xyz)
+    xyz = xyz[np.argsort(keys, kind="stable")][:n]
+    xyz = xyz[rng.permutation(xyz.shape[0])]
+    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
+
+
+def cloud_shell(n=100000, bits=10, seed=3, a=3, dups=False):
+    """Sphere-shell surface voxelised to `bits` bits (configs 3-5 shape)."""
+    rng = np.random.default_rng(seed)
+    m = int(n * (1.6 if not dups else 1.0))
+    v = rng.normal(size=(m, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    r = (1 << bits) * 0.45 * (1 + 0.1 * np.sin(5 * v[:, 0]) * np.cos(3 * v[:, 1]))
+    xyz = np.clip(np.rint(v * r[:, None] + (1 << bits) / 2), 0, (1 << bits) - 1).astype(np.int32)
+    if not dups:
+        xyz = np.unique(xyz, axis=0)
+        xyz = xyz[rng.permutation(xyz.shape[0])]
+    xyz = xyz[:n]
+    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
+
+
+def cloud_lidar(n=1000000, seed=2, a=3, scale=0.03125, lasers=64):
+    """Config 2: Ford-shaped spinning-LiDAR ring cloud, 1 mm grid scaled by
+    `scale` (positionQuantizationScale), duplicates merged."""
+    rng = np.random.default_rng(seed)
+    az_steps = (n * 115 // 100) // lasers + 1
+    theta = np.deg2rad(np.linspace(-24.8, 2.0, lasers))
+    az = np.linspace(0, 2 * np.pi, az_steps, endpoint=False)
+    T, AZ = np.meshgrid(theta, az, indexing="ij")
+    T = T.ravel()
+    AZ = AZ.ravel()
+    # range to ground plane z = -1.8 m, capped at 80 m
+    with np.errstate(divide="ignore"):
+        rng_ground = np.where(np.sin(T) < -1e-3, -1.8 / np.sin(T), 80.0)
+    r = np.minimum(rng_ground, 80.0)
+    # four box obstacles (azimuth sector, distance)
+    for a0, a1, d in ((0.3, 0.6, 12.0), (1.8, 2.3, 20.0), (3.5, 3.7, 7.0), (5.0, 5.6, 30.0)):
+        hit = (AZ > a0) & (AZ < a1) & (r * np.cos(T) > d)
+        r = np.where(hit, d / np.maximum(np.cos(T), 1e-3), r)
+    r = r + rng.normal(0, 0.01, size=r.shape)
+    x = r * np.cos(T) * np.cos(AZ)
+    y = r * np.cos(T) * np.sin(AZ)
+    z = r * np.sin(T)
+    p = np.stack([x, y, z], axis=1) * 1000.0  # mm
+    p -= p.min(axis=0)
+    xyz = np.rint(p * scale).astype(np.int32)
+    xyz = np.unique(xyz, axis=0)
+    xyz = xyz[rng.permutation(xyz.shape[0])][:n]
+    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
+
+
+def cloud_random(n, bits, seed, a=3, dup_frac=0.0, bitdepth=8):
+    """Uniform random voxels (worst case for neighbourhood structure)."""
+    rng = np.random.default_rng(seed)
+    xyz = rng.integers(0, 1 << bits, size=(n, 3), dtype=np.int32)
+    if dup_frac > 0:
+        k = int(n * dup_frac)
+        src = rng.integers(0, n, size=k)
+        dst = rng.integers(0, n, size=k)
+        xyz[dst] = xyz[src]
+    attrs = rng.integers(0, 1 << bitdepth, size=(n, a), dtype=np.int32)
+    return xyz, attrs

@@ -1,0 +1,134 @@
+"""CPU tests: the oracle (oracle/raht_oracle.c) against (a) the committed
+golden vectors produced by the unmodified reference and (b), when the
+compiled reference is present (oracle/_ref), the reference run live on a
+wider set of clouds and flag combinations."""
+import os
+
+import numpy as np
+import pytest
+
+from pcc_testlib import *  # noqa
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+from golden.make_golden import VARIANTS  # noqa
+
+
+@pytest.fixture(scope="module")
+def raht_gold():
+    return np.load(os.path.join(GOLD, "raht_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def arith_gold():
+    return np.load(os.path.join(GOLD, "arith_golden.npz"))
+
+
+def test_arith_golden(arith_gold):
+    g = arith_gold
+    o = load_oracle()
+    assert [o.oracle_isqrt(int(x)) for x in g["xs"]] == g["isqrt"].tolist()
+    assert [o.oracle_irsqrt(int(x)) for x in g["xs"]] == g["irsqrt"].tolist()
+    assert [o.oracle_fixed_mul(int(a), int(b)) for a, b in zip(g["fa"], g["fb"])] == g["fxmul"].tolist()
+    assert [o.oracle_quantize(int(q), int(x)) for q, x in zip(g["qps"], g["qx"])] == g["quant"].tolist()
+    assert [o.oracle_scale(int(q), int(x)) for q, x in zip(g["qps"], g["qx"])] == g["scale"].tolist()
+    assert [o.oracle_morton_addr(*map(int, p)) for p in g["pts"]] == g["morton"].tolist()
+    assert [o.oracle_morton3d_add(int(a), int(b)) for a, b in zip(g["ma"], g["mb"])] == g["madd"].tolist()
+    assert [o.oracle_div_approx(int(a), int(b), 0) for a, b in zip(g["da"], g["db"])] == g["divapprox"].tolist()
+    assert np.array_equal(np_morton(g["pts"]), g["morton"])
+
+
+@pytest.mark.parametrize("cname", ["cube", "shell", "shelldup", "lidar", "sparse21"])
+def test_raht_golden(raht_gold, cname):
+    g = raht_gold
+    xyz, attrs = g[f"{cname}/xyz"], g[f"{cname}/attrs"]
+    qpo = g[f"{cname}/qpo"] if f"{cname}/qpo" in g else None
+    mort, a_s, order = sort_cloud(xyz, attrs)
+    k2, o2 = oracle_morton_sort(xyz)
+    assert np.array_equal(k2, mort) and np.array_equal(o2, order)
+    q = qpo[order] if qpo is not None else None
+    for vname, kw in VARIANTS.items():
+        for qp in (16, 34):
+            p, qs = make_params(**kw), make_qpset(qp=qp)
+            rec, coef = oracle_raht(1, p, qs, mort, a_s, qpoffs=q)
+            assert np.array_equal(coef, g[f"{cname}/{vname}/qp{qp}/coef"]), (vname, qp)
+            assert np.array_equal(rec, g[f"{cname}/{vname}/qp{qp}/rec"]), (vname, qp)
+            rec2, _ = oracle_raht(0, p, qs, mort, a_s * 0, coeffs=coef, qpoffs=q)
+            assert np.array_equal(rec2, rec), (vname, qp)
+
+
+needs_ref = pytest.mark.skipif(not ref_available(), reason="compiled reference (oracle/_ref) not present")
+
+
+def _cmp(xyz, attrs, p, qs, qpo=None):
+    mort, a_s, order = sort_cloud(xyz, attrs)
+    q = qpo[order] if qpo is not None else None
+    rr, rc = ref_raht(1, p, qs, mort, a_s, qpoffs=q)
+    orr, oc = oracle_raht(1, p, qs, mort, a_s, qpoffs=q)
+    assert np.array_equal(rc, oc)
+    assert np.array_equal(rr, orr)
+    r2, _ = ref_raht(0, p, qs, mort, a_s * 0, coeffs=rc, qpoffs=q)
+    o2, _ = oracle_raht(0, p, qs, mort, a_s * 0, coeffs=rc, qpoffs=q)
+    assert np.array_equal(r2, o2)
+    assert np.array_equal(r2, rr)  # decoder reproduces the encoder's reconstruction
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(), dict(prediction=0), dict(subnode=0), dict(haar=1),
+                                dict(ext=0), dict(ext=0, subnode=0), dict(thr0=0, thr1=1)])
+@pytest.mark.parametrize("qp", [10, 34, 46])
+def test_live_shell(kw, qp):
+    xyz, attrs = cloud_shell(30000, bits=8, seed=qp)
+    _cmp(xyz, attrs, make_params(**kw), make_qpset(qp=qp))
+
+
+@needs_ref
+@pytest.mark.parametrize("a", [1, 3])
+def test_live_dups_and_lidar(a):
+    xyz, attrs = cloud_shell(30000, bits=7, seed=4, a=a, dups=True)
+    for kw in (dict(), dict(haar=1), dict(ext=0)):
+        _cmp(xyz, attrs, make_params(**kw), make_qpset(qp=28))
+    xyz, attrs = cloud_lidar(40000, seed=2, a=a)
+    _cmp(xyz, attrs, make_params(search_range=2500), make_qpset(qp=34))
+    xyz, attrs = cloud_random(20000, 3, seed=12, a=a)  # weights > 1024
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=34))
+
+
+@needs_ref
+def test_live_qp_structures():
+    rng = np.random.default_rng(7)
+    xyz, attrs = cloud_shell(30000, bits=8, seed=5)
+    qpo = rng.integers(-6, 7, size=(xyz.shape[0], 2)).astype(np.int32)
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=30), qpo)
+    _cmp(xyz, attrs, make_params(), make_qpset(layers=[(40, -2), (36, -1), (32, 0), (28, 1), (26, 2)]))
+    ac = [[(l - c, c - l) for c in range(7)] for l in range(4)]
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=30, ac_qps=ac), qpo)
+    xyz, a16 = cloud_random(20000, 8, seed=11, bitdepth=16)
+    _cmp(xyz, a16, make_params(), make_qpset(qp=40, bitdepth=16))
+
+
+@needs_ref
+def test_live_edge_cases():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 9, 17):
+        xyz, attrs = cloud_random(n, 3, seed=n)
+        _cmp(xyz, attrs, make_params(), make_qpset(qp=20))
+    xyz = np.tile(np.array([[5, 6, 7]], dtype=np.int32), (6, 1))
+    attrs = rng.integers(0, 256, size=(6, 3)).astype(np.int32)
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=20))  # every point identical
+    xyz = np.array([[0, 0, 0], [2**20, 2**20, 2**20], [2**20 + 1, 2**20, 2**20]], dtype=np.int32)
+    _cmp(xyz, attrs[:3], make_params(thr0=0, thr1=0), make_qpset(qp=20))  # skipped stages
+    for bits in (4, 12, 21):
+        xyz, attrs = cloud_random(10000, bits, seed=bits, dup_frac=0.2)
+        _cmp(xyz, attrs, make_params(thr0=0, thr1=1), make_qpset(qp=30))
+
+
+@needs_ref
+def test_live_scalar_helpers():
+    o, r = load_oracle(), load_ref()
+    rng = np.random.default_rng(5)
+    for x in list(range(0, 3000)) + [int(v) for v in rng.integers(0, 1 << 62, size=3000, dtype=np.uint64)]:
+        assert o.oracle_isqrt(x) == r.tmc13ref_isqrt(x)
+        assert o.oracle_irsqrt(x) == r.tmc13ref_irsqrt(x)
+    # kDivApproxDivisor[i] + 1 == 65536 // (i + 1) for every index the LUT serves
+    for b in range(1, 257):
+        assert o.oracle_div_approx(1 << 20, b, 0) == r.tmc13ref_div_approx(1 << 20, b, 0)
