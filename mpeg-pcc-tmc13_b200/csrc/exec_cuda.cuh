@@ -1,0 +1,334 @@
+// exec_cuda.cuh — the CUDA executor: turns the per-item bodies of
+// raht_core.cuh into kernel launches on one stream of one B200.
+//
+//   foreach  : grid-stride kernel, grid sized in multiples of the SM count
+//   ordered  : block-level dataflow kernel.  CTAs claim chunks of the index
+//              space in ascending order through a global ticket, so every
+//              index below a running CTA's chunk is owned by a CTA that is
+//              already running: an item may spin on flags published by any
+//              lower index without risk of deadlock, whatever the residency.
+//   compact  : three-kernel stream compaction (tile counts, scan of the tile
+//              counts, in-tile scan + emit); ranks are exact and ordered.
+//
+// Workspace comes from a per-context arena (one cudaMalloc in steady state).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <vector>
+
+namespace pccb200 {
+
+extern std::atomic<uint64_t> g_launchCount;
+
+struct CudaError {
+  cudaError_t code;
+  const char* what;
+};
+
+#define PCC_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess)                                     \
+      throw ::pccb200::CudaError{_e, #expr};                   \
+  } while (0)
+
+//----------------------------------------------------------------------------
+
+class Arena {
+public:
+  ~Arena() { release(); }
+
+  void* alloc(size_t bytes)
+  {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (chunks_.empty() || used_ + bytes > chunks_.back().size) {
+      size_t want = bytes > nextSize_ ? bytes : nextSize_;
+      void* p = nullptr;
+      PCC_CUDA_CHECK(cudaMalloc(&p, want));
+      chunks_.push_back({p, want});
+      total_ += want;
+      used_ = 0;
+    }
+    void* r = static_cast<char*>(chunks_.back().ptr) + used_;
+    used_ += bytes;
+    high_ += bytes;
+    return r;
+  }
+
+  // start of a call: fold everything into one chunk big enough for the
+  // largest call seen so far
+  void reset()
+  {
+    if (high_ > peak_)
+      peak_ = high_;
+    if (chunks_.size() > 1 || (chunks_.size() == 1 && chunks_[0].size < peak_)) {
+      release();
+    }
+    if (chunks_.empty() && peak_) {
+      void* p = nullptr;
+      size_t want = peak_ + (peak_ >> 3) + (1 << 20);
+      PCC_CUDA_CHECK(cudaMalloc(&p, want));
+      chunks_.push_back({p, want});
+      total_ = want;
+    }
+    used_ = 0;
+    high_ = 0;
+  }
+
+  void release()
+  {
+    for (auto& c : chunks_)
+      cudaFree(c.ptr);
+    chunks_.clear();
+    total_ = 0;
+    used_ = 0;
+  }
+
+private:
+  struct Chunk {
+    void* ptr;
+    size_t size;
+  };
+  std::vector<Chunk> chunks_;
+  size_t used_ = 0;
+  size_t total_ = 0;
+  size_t high_ = 0;
+  size_t peak_ = 0;
+  size_t nextSize_ = size_t(64) << 20;
+};
+
+//----------------------------------------------------------------------------
+// kernels
+
+template<class F>
+__global__ void __launch_bounds__(256)
+k_foreach(F f, int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x)
+    f(i);
+}
+
+constexpr int kOrderedThreads = 128;
+
+template<class F>
+__global__ void __launch_bounds__(kOrderedThreads)
+k_ordered(F f, int64_t n, unsigned long long* ticket)
+{
+  __shared__ unsigned long long sBase;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nWarps = kOrderedThreads / 32;
+  for (;;) {
+    if (threadIdx.x == 0)
+      sBase = atomicAdd(ticket, (unsigned long long)kOrderedThreads);
+    __syncthreads();
+    const int64_t base = int64_t(sBase);
+    __syncthreads();
+    if (base >= n)
+      return;
+    // lanes of one warp take items nWarps apart so that directly adjacent
+    // items (the commonest dependency) sit in different warps
+    const int64_t i = base + lane * nWarps + warp;
+    if (i < n)
+      f(i);
+  }
+}
+
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = 8;
+constexpr int kTile = kTileThreads * kTileItems;
+
+template<class P>
+__global__ void __launch_bounds__(kTileThreads)
+k_tile_count(P pred, int64_t n, int* tileCount)
+{
+  const int64_t base = int64_t(blockIdx.x) * kTile + threadIdx.x * kTileItems;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < kTileItems; j++)
+    if (base + j < n && pred(base + j))
+      c++;
+  // block reduce
+  __shared__ int sWarp[kTileThreads / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0)
+    sWarp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kTileThreads / 32; w++)
+      t += sWarp[w];
+    tileCount[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the tile counts by a single CTA (tile counts are few:
+// n / 2048)
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(int* tileCount, int numTiles)
+{
+  __shared__ int sWarp[32];
+  __shared__ int sCarry;
+  if (threadIdx.x == 0)
+    sCarry = 0;
+  __syncthreads();
+  for (int base = 0; base < numTiles; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < numTiles ? tileCount[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o)
+        x += y;
+    }
+    if ((threadIdx.x & 31) == 31)
+      sWarp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int s = sWarp[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, s, o);
+        if (threadIdx.x >= o)
+          s += y;
+      }
+      sWarp[threadIdx.x] = s;
+    }
+    __syncthreads();
+    int warpOff = (threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1] : 0;
+    int carry = sCarry;
+    if (i < numTiles)
+      tileCount[i] = carry + warpOff + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023)
+      sCarry = carry + warpOff + x;
+    __syncthreads();
+  }
+}
+
+template<class P, class E>
+__global__ void __launch_bounds__(kTileThreads)
+k_tile_emit(P pred, E emit, int64_t n, const int* tileOffset)
+{
+  const int64_t base = int64_t(blockIdx.x) * kTile + threadIdx.x * kTileItems;
+  unsigned flags = 0;
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < kTileItems; j++)
+    if (base + j < n && pred(base + j)) {
+      flags |= 1u << j;
+      c++;
+    }
+  // exclusive scan of c over the CTA
+  __shared__ int sWarp[kTileThreads / 32];
+  int x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o)
+      x += y;
+  }
+  if ((threadIdx.x & 31) == 31)
+    sWarp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  int warpOff = 0;
+  for (int w = 0; w < (threadIdx.x >> 5); w++)
+    warpOff += sWarp[w];
+  int64_t rank = int64_t(tileOffset[blockIdx.x]) + warpOff + x - c;
+#pragma unroll
+  for (int j = 0; j < kTileItems; j++)
+    if ((flags >> j) & 1)
+      emit(rank++, base + j);
+}
+
+//----------------------------------------------------------------------------
+
+struct DeviceExec {
+  cudaStream_t stream = nullptr;
+  Arena* arena = nullptr;
+  int numSMs = 148;
+  unsigned long long* ticket = nullptr;  // device word for ordered launches
+
+  template<class T>
+  T* alloc(size_t n)
+  {
+    return static_cast<T*>(arena->alloc((n ? n : 1) * sizeof(T)));
+  }
+
+  void zero(void* p, size_t bytes)
+  {
+    PCC_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
+  }
+
+  void upload(void* dst, const void* src, size_t bytes)
+  {
+    // small parameter blocks: the source may be a stack temporary, so the
+    // copy must have completed (or been staged) when this returns.  Pageable
+    // sources make cudaMemcpyAsync stage synchronously.
+    PCC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+  }
+
+  void download(void* dst, const void* src, size_t bytes)
+  {
+    PCC_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    PCC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+
+  template<class F>
+  void foreach(int64_t n, const F& f)
+  {
+    if (n <= 0)
+      return;
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = int64_t(numSMs) * 16;
+    if (blocks > cap)
+      blocks = cap;
+    k_foreach<F><<<unsigned(blocks), 256, 0, stream>>>(f, n);
+    g_launchCount++;
+    PCC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  template<class F>
+  void ordered(int64_t n, const F& f)
+  {
+    if (n <= 0)
+      return;
+    PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    int perSM = 0;
+    PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &perSM, k_ordered<F>, kOrderedThreads, 0));
+    if (perSM < 1)
+      perSM = 1;
+    int64_t blocks = (n + kOrderedThreads - 1) / kOrderedThreads;
+    int64_t cap = int64_t(numSMs) * perSM;
+    if (blocks > cap)
+      blocks = cap;
+    k_ordered<F><<<unsigned(blocks), kOrderedThreads, 0, stream>>>(f, n, ticket);
+    g_launchCount++;
+    PCC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  template<class P, class E>
+  void compact(int64_t n, const P& pred, const E& emit)
+  {
+    if (n <= 0)
+      return;
+    int numTiles = int((n + kTile - 1) / kTile);
+    int* tiles = alloc<int>(numTiles);
+    k_tile_count<P><<<numTiles, kTileThreads, 0, stream>>>(pred, n, tiles);
+    k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, numTiles);
+    k_tile_emit<P, E><<<numTiles, kTileThreads, 0, stream>>>(pred, emit, n, tiles);
+    g_launchCount += 3;
+    PCC_CUDA_CHECK(cudaGetLastError());
+  }
+};
+
+}  // namespace pccb200

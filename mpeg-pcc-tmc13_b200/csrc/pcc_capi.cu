@@ -1,0 +1,419 @@
+// pcc_capi.cu — the C ABI (include/pcc_attr_b200.h) over the CUDA kernels.
+//
+// Every entry point: validate, stage the caller's host arrays into HBM, run
+// the kernels on the context's stream, copy results back, synchronise.  No
+// CPU implementation exists behind this ABI: without a usable sm_100 device
+// every compute entry point returns PCCB200_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "exec_cuda.cuh"
+#include "lifting.cuh"
+#include "morton_sort.cuh"
+#include "pcc_attr_b200.h"
+#include "raht_pipeline.cuh"
+
+namespace pccb200 {
+
+std::atomic<uint64_t> g_launchCount{0};
+
+namespace {
+
+thread_local std::string t_lastError;
+
+struct Context {
+  std::mutex mu;
+  int device = 0;
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  unsigned long long* ticket = nullptr;
+  int numSMs = 0;
+};
+
+Context&
+ctx()
+{
+  static Context c;
+  return c;
+}
+
+int
+fail(int code, const std::string& msg)
+{
+  t_lastError = msg;
+  return code;
+}
+
+// returns PCCB200_OK or an error; must hold c.mu
+int
+ensure_ready(Context& c)
+{
+  if (c.ready)
+    return PCCB200_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(PCCB200_ERR_NO_DEVICE,
+                std::string("no CUDA device: ") + cudaGetErrorString(e));
+  }
+  if (c.device >= count)
+    return fail(PCCB200_ERR_NO_DEVICE, "device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, c.device);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(PCCB200_ERR_NO_DEVICE,
+                std::string("kernels are built for sm_100a only; device is ") + prop.name);
+  e = cudaSetDevice(c.device);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
+  e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
+  e = cudaMalloc(&c.ticket, 256);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_NOMEM, cudaGetErrorString(e));
+  c.numSMs = prop.multiProcessorCount;
+  c.ready = true;
+  return PCCB200_OK;
+}
+
+DeviceExec
+make_exec(Context& c)
+{
+  DeviceExec ex;
+  ex.stream = c.stream;
+  ex.arena = &c.arena;
+  ex.numSMs = c.numSMs;
+  ex.ticket = c.ticket;
+  return ex;
+}
+
+template<class T>
+T*
+to_device(DeviceExec& ex, const T* host, size_t n)
+{
+  T* d = ex.alloc<T>(n);
+  if (n)
+    PCC_CUDA_CHECK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ex.stream));
+  return d;
+}
+
+template<class T>
+void
+to_host(DeviceExec& ex, T* host, const T* dev, size_t n)
+{
+  if (n)
+    PCC_CUDA_CHECK(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ex.stream));
+}
+
+// runs body(ex) with the context locked and CUDA errors mapped to a status
+template<class Body>
+int
+with_device(Body body)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  int rc = ensure_ready(c);
+  if (rc != PCCB200_OK)
+    return rc;
+  try {
+    PCC_CUDA_CHECK(cudaSetDevice(c.device));
+    c.arena.reset();
+    DeviceExec ex = make_exec(c);
+    rc = body(ex);
+    PCC_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (rc != PCCB200_OK && t_lastError.empty())
+      t_lastError = "invalid argument";
+    return rc;
+  } catch (const CudaError& e) {
+    cudaGetLastError();
+    return fail(e.code == cudaErrorMemoryAllocation ? PCCB200_ERR_NOMEM : PCCB200_ERR_CUDA,
+                std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  }
+}
+
+int
+raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset* qpset,
+            const int32_t* qpo, const int64_t* morton, int32_t* attrs, int A, int n,
+            int32_t* coeffs)
+{
+  if (!params || !qpset || !morton || !attrs || !coeffs || n <= 0 || A < 1 || A > 3)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    int64_t* dKeys = to_device(ex, morton, size_t(n));
+    int32_t* dAttrs = forward ? to_device(ex, attrs, size_t(n) * A)
+                              : ex.alloc<int32_t>(size_t(n) * A);
+    int32_t* dQpo = qpo ? to_device(ex, qpo, size_t(n) * 2) : nullptr;
+    int32_t* dCoef = forward ? ex.alloc<int32_t>(size_t(n) * A)
+                             : to_device(ex, coeffs, size_t(n) * A);
+    int rc = raht_run(ex, *params, *qpset, forward, dKeys, dAttrs, dQpo, dCoef,
+                      int64_t(n), A, n);
+    if (rc != PCCB200_OK)
+      return fail(rc, rc == PCCB200_ERR_UNSORTED ? "morton codes not ascending"
+                                                 : "invalid parameters");
+    to_host(ex, attrs, dAttrs, size_t(n) * A);
+    if (forward)
+      to_host(ex, coeffs, dCoef, size_t(n) * A);
+    return PCCB200_OK;
+  });
+}
+
+int
+attr_raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                 const int32_t* qpo, const int32_t* xyz, int32_t* attrs, int A,
+                 int bitdepth, const int64_t* sliceOffsets, int numSlices,
+                 int32_t* coeffs)
+{
+  if (!params || !qpset || !xyz || !attrs || !coeffs || !sliceOffsets || numSlices <= 0
+      || A < 1 || A > 3 || bitdepth < 1 || bitdepth > 16)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  const int64_t total = sliceOffsets[numSlices];
+  for (int s = 0; s < numSlices; s++) {
+    int64_t len = sliceOffsets[s + 1] - sliceOffsets[s];
+    if (len <= 0 || len > INT32_MAX)
+      return fail(PCCB200_ERR_INVALID_ARG, "empty or oversized slice");
+  }
+  return with_device([&](DeviceExec& ex) -> int {
+    int32_t* dXyz = to_device(ex, xyz, size_t(total) * 3);
+    int32_t* dAttrsIn = forward ? to_device(ex, attrs, size_t(total) * A)
+                                : ex.alloc<int32_t>(size_t(total) * A);
+    int32_t* dQpoIn = qpo ? to_device(ex, qpo, size_t(total) * 2) : nullptr;
+    int32_t* dCoef = forward ? ex.alloc<int32_t>(size_t(total) * A)
+                             : to_device(ex, coeffs, size_t(total) * A);
+    int64_t* dKeys = ex.alloc<int64_t>(size_t(total));
+    int32_t* dOrder = ex.alloc<int32_t>(size_t(total));
+    int32_t* dAttrs = ex.alloc<int32_t>(size_t(total) * A);
+    int32_t* dQpo = qpo ? ex.alloc<int32_t>(size_t(total) * 2) : nullptr;
+    int32_t* dOut = ex.alloc<int32_t>(size_t(total) * A);
+    const int32_t clipMax = (1 << bitdepth) - 1;
+    for (int s = 0; s < numSlices; s++) {
+      const int64_t o = sliceOffsets[s];
+      const int n = int(sliceOffsets[s + 1] - o);
+      device_morton_sort(ex, dXyz + 3 * o, n, dKeys + o, dOrder + o);
+      const unsigned g = grid_for(n, ex.numSMs);
+      if (forward) {
+        k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dAttrsIn + o * A, dOrder + o, n, A,
+                                                         dAttrs + o * A);
+        g_launchCount++;
+      }
+      if (qpo) {
+        k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dQpoIn + 2 * o, dOrder + o, n, 2,
+                                                         dQpo + 2 * o);
+        g_launchCount++;
+      }
+      int rc = raht_run(ex, *params, *qpset, forward, dKeys + o, dAttrs + o * A,
+                        qpo ? dQpo + 2 * o : nullptr, dCoef + o, total, A, n);
+      if (rc != PCCB200_OK)
+        return fail(rc, "invalid parameters");
+      k_scatter_rows_clip<<<g, 256, 0, ex.stream>>>(dAttrs + o * A, dOrder + o, n, A, clipMax,
+                                                    dOut + o * A);
+      g_launchCount++;
+    }
+    PCC_CUDA_CHECK(cudaGetLastError());
+    to_host(ex, attrs, dOut, size_t(total) * A);
+    if (forward)
+      to_host(ex, coeffs, dCoef, size_t(total) * A);
+    return PCCB200_OK;
+  });
+}
+
+}  // namespace
+}  // namespace pccb200
+
+using namespace pccb200;
+
+extern "C" {
+
+void
+pccb200_raht_set_prediction_weights(pccb200_raht_params* p, const int32_t w[5])
+{
+  const int child[12] = {4, 4, 3, 4, 3, 3, 4, 4, 4, 4, 4, 4};
+  const int parent[19] = {0, 1, 1, 1, 2, 2, 2, 2, 2, 1, 2, 1, 1, 2, 2, 2, 2, 2, 2};
+  for (int i = 0; i < 12; i++)
+    p->pred_weight_child[i] = w[child[i]];
+  for (int i = 0; i < 19; i++)
+    p->pred_weight_parent[i] = w[parent[i]];
+}
+
+void
+pccb200_raht_params_default(pccb200_raht_params* p)
+{
+  p->prediction_enabled = 1;
+  p->integer_haar = 0;
+  p->prediction_threshold0 = 2;
+  p->prediction_threshold1 = 6;
+  p->subnode_prediction_enabled = 1;
+  p->prediction_search_range = 50000;
+  p->raht_extension = 1;
+  const int32_t w[5] = {9, 3, 1, 5, 2};
+  pccb200_raht_set_prediction_weights(p, w);
+}
+
+int
+pccb200_abi_version(void)
+{
+  return PCCB200_ABI_VERSION;
+}
+
+int
+pccb200_set_device(int device)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (device < 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "negative device index");
+  if (c.ready && device != c.device) {
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    c.arena.release();
+    cudaFree(c.ticket);
+    cudaStreamDestroy(c.stream);
+    c.ready = false;
+  }
+  c.device = device;
+  return ensure_ready(c);
+}
+
+const char*
+pccb200_last_error(void)
+{
+  return t_lastError.c_str();
+}
+
+uint64_t
+pccb200_kernel_launch_count(void)
+{
+  return g_launchCount.load();
+}
+
+int
+pccb200_morton_sort(const int32_t* xyz, int32_t n, int64_t* keys_out, int32_t* order_out)
+{
+  if (!xyz || !keys_out || !order_out || n <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    int64_t* dKeys = ex.alloc<int64_t>(n);
+    int32_t* dOrder = ex.alloc<int32_t>(n);
+    device_morton_sort(ex, dXyz, n, dKeys, dOrder);
+    to_host(ex, keys_out, dKeys, size_t(n));
+    to_host(ex, order_out, dOrder, size_t(n));
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_raht_forward(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                     const int32_t* point_qp_offsets, const int64_t* morton,
+                     int32_t* attrs_inout, int32_t num_attrs, int32_t n,
+                     int32_t* coeffs_out)
+{
+  return raht_common(true, params, qpset, point_qp_offsets, morton, attrs_inout, num_attrs, n,
+                     coeffs_out);
+}
+
+int
+pccb200_raht_inverse(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                     const int32_t* point_qp_offsets, const int64_t* morton,
+                     int32_t* attrs_out, int32_t num_attrs, int32_t n,
+                     const int32_t* coeffs_in)
+{
+  return raht_common(false, params, qpset, point_qp_offsets, morton, attrs_out, num_attrs, n,
+                     const_cast<int32_t*>(coeffs_in));
+}
+
+int
+pccb200_attr_raht_encode(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                         const int32_t* point_qp_offsets, const int32_t* xyz,
+                         int32_t* attrs_inout, int32_t num_attrs, int32_t n, int32_t bitdepth,
+                         int32_t* coeffs_out)
+{
+  const int64_t offs[2] = {0, n};
+  return attr_raht_common(true, params, qpset, point_qp_offsets, xyz, attrs_inout, num_attrs,
+                          bitdepth, offs, 1, coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                         const int32_t* point_qp_offsets, const int32_t* xyz,
+                         int32_t* attrs_out, int32_t num_attrs, int32_t n, int32_t bitdepth,
+                         const int32_t* coeffs_in)
+{
+  const int64_t offs[2] = {0, n};
+  return attr_raht_common(false, params, qpset, point_qp_offsets, xyz, attrs_out, num_attrs,
+                          bitdepth, offs, 1, const_cast<int32_t*>(coeffs_in));
+}
+
+int
+pccb200_attr_raht_encode_slices(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                                const int32_t* point_qp_offsets, const int32_t* xyz,
+                                int32_t* attrs_inout, int32_t num_attrs, int32_t bitdepth,
+                                const int64_t* slice_offsets, int32_t num_slices,
+                                int32_t* coeffs_out)
+{
+  return attr_raht_common(true, params, qpset, point_qp_offsets, xyz, attrs_inout, num_attrs,
+                          bitdepth, slice_offsets, num_slices, coeffs_out);
+}
+
+int
+pccb200_quant_weights(const pccb200_predictor* preds, int32_t n,
+                      const uint32_t* num_points_in_lod, int32_t lod_count, uint64_t* qw_out)
+{
+  if (!preds || !num_points_in_lod || !qw_out || n <= 0 || lod_count <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    pccb200_predictor* dP = to_device(ex, preds, size_t(n));
+    uint64_t* dQw = ex.alloc<uint64_t>(n);
+    int rc = run_quant_weights(ex, dP, n, num_points_in_lod, lod_count, dQw);
+    if (rc != PCCB200_OK)
+      return fail(rc, "numPointsInLod does not partition [0, n)");
+    to_host(ex, qw_out, dQw, size_t(n));
+    return PCCB200_OK;
+  });
+}
+
+static int
+lift_common(bool forward, const pccb200_predictor* preds, const uint64_t* qw, int32_t n,
+            const uint32_t* num_points_in_lod, int32_t lod_count, int64_t* attrs, int32_t A)
+{
+  if (!preds || !qw || !num_points_in_lod || !attrs || n <= 0 || lod_count <= 0
+      || (A != 1 && A != 3))
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    pccb200_predictor* dP = to_device(ex, preds, size_t(n));
+    uint64_t* dQw = to_device(ex, qw, size_t(n));
+    int64_t* dA = to_device(ex, attrs, size_t(n) * A);
+    int rc = run_lift(ex, forward, dP, dQw, n, num_points_in_lod, lod_count, dA, A);
+    if (rc != PCCB200_OK)
+      return fail(rc, rc == PCCB200_ERR_UNSUPPORTED
+                        ? "a predictor references its own level of detail"
+                        : "numPointsInLod does not partition [0, n)");
+    to_host(ex, attrs, dA, size_t(n) * A);
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_lift_forward(const pccb200_predictor* preds, const uint64_t* qw, int32_t n,
+                     const uint32_t* num_points_in_lod, int32_t lod_count,
+                     int64_t* attrs_inout, int32_t num_attrs)
+{
+  return lift_common(true, preds, qw, n, num_points_in_lod, lod_count, attrs_inout, num_attrs);
+}
+
+int
+pccb200_lift_inverse(const pccb200_predictor* preds, const uint64_t* qw, int32_t n,
+                     const uint32_t* num_points_in_lod, int32_t lod_count,
+                     int64_t* attrs_inout, int32_t num_attrs)
+{
+  return lift_common(false, preds, qw, n, num_points_in_lod, lod_count, attrs_inout, num_attrs);
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// raht_pipeline.cuh — the host-side schedule of one RAHT call, written
+// against an executor so that the same schedule drives CUDA kernels
+// (exec_cuda.cuh: DeviceExec) and, for the CPU unit tests of the kernel
+// bodies, plain loops (tests/emu/exec_host.h: HostExec).
+//
+// Executor concept:
+//   T*   alloc<T>(size_t n)                 workspace memory (uninitialised)
+//   void zero(void* p, size_t bytes)
+//   void upload(void* dst, const void* src, size_t bytes)      host -> exec
+//   void download(void* dst, const void* src, size_t bytes)    exec -> host, synchronous
+//   void foreach(int64_t n, F f)            f(i) for i in [0, n), any order
+//   void ordered(int64_t n, F f)            f(i) with block-level dataflow:
+//                                           f may spin on flags set by f(j), j < i
+//   void compact(int64_t n, Pred p, Emit e) e(rank, i) for every i with p(i),
+//                                           rank = number of j < i with p(j)
+//
+// Mirrors the control flow of uraht_process (tmc3/RAHT.cpp:977-1976).
+#pragma once
+
+#include <vector>
+
+#include "raht_core.cuh"
+
+namespace pccb200 {
+
+struct StagePlan {
+  int level;
+  int n;
+};
+
+// Stage levels from the adjacent-key histogram: every third binary level
+// below the first level at which all points agree; a level that adds no
+// nodes with respect to the level above is skipped (RAHT.cpp:1086,1205-1209).
+// Returns the stages fine -> coarse; empty when all points coincide.
+inline std::vector<StagePlan>
+plan_stages(const int hist[64], int& nLeaves)
+{
+  int64_t total = 0;
+  int top = -1;
+  for (int h = 0; h < 64; h++) {
+    total += hist[h];
+    if (hist[h])
+      top = h;
+  }
+  nLeaves = int(total + 1);
+  std::vector<StagePlan> stages;
+  if (top < 0)
+    return stages;
+  const int lmax = top + 1;
+  const int rootLevel = 3 * ((lmax - 1) / 3);
+  auto count = [&](int s) {
+    int64_t c = 1;
+    for (int h = s; h < 64; h++)
+      c += hist[h];
+    return int(c);
+  };
+  for (int s = 0; s <= rootLevel; s += 3) {
+    int c = count(s);
+    if (s == rootLevel || c != count(s + 3)) {
+      if (stages.empty())
+        c = nLeaves;  // the finest processed stage holds the leaves
+      stages.push_back({s, c});
+    }
+  }
+  return stages;
+}
+
+template<class Exec>
+Stage
+alloc_stage(Exec& ex, int level, int n, int A, bool hasQp, bool needRec)
+{
+  Stage s;
+  s.level = level;
+  s.n = n;
+  s.key = ex.template alloc<int64_t>(n);
+  s.weight = ex.template alloc<int32_t>(n);
+  s.attr = ex.template alloc<int32_t>(size_t(n) * A);
+  s.qpUp = hasQp ? ex.template alloc<int32_t>(size_t(n) * 2) : nullptr;
+  s.qpDown = hasQp ? ex.template alloc<int32_t>(size_t(n) * 2) : nullptr;
+  s.first = ex.template alloc<int32_t>(size_t(n) + 1);
+  s.nn = ex.template alloc<int32_t>(n);
+  s.occ = ex.template alloc<uint8_t>(n);
+  s.rec = needRec ? ex.template alloc<int64_t>(size_t(n) * A) : nullptr;
+  s.recUs = needRec ? ex.template alloc<int64_t>(size_t(n) * A) : nullptr;
+  s.done = ex.template alloc<int>(n);
+  return s;
+}
+
+inline RahtConfig
+make_config(const pccb200_raht_params& pp, const pccb200_qpset& qs, bool forward,
+            int A, bool hasQp)
+{
+  RahtConfig c;
+  c.A = A;
+  c.isEncoder = forward;
+  c.ext = pp.raht_extension != 0;
+  c.haar = pp.integer_haar != 0;
+  c.hasQp = hasQp;
+  c.predictionEnabled = pp.prediction_enabled != 0;
+  c.subnode = pp.subnode_prediction_enabled != 0;
+  c.thr0 = pp.prediction_threshold0;
+  c.thr1 = pp.prediction_threshold1;
+  c.searchRange = pp.prediction_search_range;
+  for (int i = 0; i < 19; i++)
+    c.predWeightParent[i] = pp.pred_weight_parent[i];
+  for (int i = 0; i < 12; i++)
+    c.predWeightChild[i] = pp.pred_weight_child[i];
+  c.numLayers = qs.num_layers;
+  c.maxQp = qs.max_qp;
+  c.fixedPointQpOffset = qs.fixed_point_qp_offset;
+  c.numAcLayers = qs.num_ac_coeff_qp_layers;
+  return c;
+}
+
+// keys / attrs / qpo / coef live in executor memory.  attrs: N*A in, out.
+// coef: component k at coef + k*coefStride.  Returns a PCCB200_* status.
+template<class Exec>
+int
+raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
+         bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo,
+         int32_t* coef, int64_t coefStride, int A, int N)
+{
+  if (N <= 0 || A < 1 || A > 3 || qs.num_layers < 1
+      || qs.num_layers > PCCB200_MAX_QP_LAYERS
+      || qs.num_ac_coeff_qp_layers > PCCB200_MAX_AC_QP_LAYERS
+      || qs.num_ac_coeff_qp_layers < 0)
+    return PCCB200_ERR_INVALID_ARG;
+
+  const bool hasQp = qpo != nullptr;
+  RahtConfig cfg = make_config(pp, qs, forward, A, hasQp);
+
+  QpTables hostQt;
+  for (int i = 0; i < PCCB200_MAX_QP_LAYERS; i++) {
+    hostQt.layers[i][0] = qs.layers[i][0];
+    hostQt.layers[i][1] = qs.layers[i][1];
+  }
+  for (int l = 0; l < PCCB200_MAX_AC_QP_LAYERS; l++)
+    for (int c = 0; c < 7; c++) {
+      hostQt.acQps[l][c][0] = qs.ac_coeff_qps[l][c][0];
+      hostQt.acQps[l][c][1] = qs.ac_coeff_qps[l][c][1];
+    }
+  QpTables* qt = ex.template alloc<QpTables>(1);
+  ex.upload(qt, &hostQt, sizeof(QpTables));
+
+  if (N == 1) {
+    ex.foreach(1, SinglePointFn{cfg, qt, qpo, attrs, coef, coefStride});
+    return PCCB200_OK;
+  }
+
+  //-- adjacent-key statistics (one small synchronising read-back per call)
+  int* dHist = ex.template alloc<int>(65);
+  ex.zero(dHist, 65 * sizeof(int));
+  ex.foreach(N, LevelHistFn{keys, dHist});
+  int hist[65];
+  ex.download(hist, dHist, sizeof(hist));
+  if (hist[64])
+    return PCCB200_ERR_UNSORTED;
+
+  int nLeaves = 0;
+  std::vector<StagePlan> plan = plan_stages(hist, nLeaves);
+  const bool hasStages = !plan.empty();
+  const int numDup = N - nLeaves;
+
+  //-- leaves
+  std::vector<Stage> stages;
+  Stage L = alloc_stage(ex, hasStages ? plan[0].level : 0, nLeaves, A, hasQp, true);
+  stages.push_back(L);
+  ex.compact(N, LeafHead{keys}, StageEmit{keys, L.key, L.first});
+  {
+    int32_t n32 = N;
+    ex.upload(L.first + nLeaves, &n32, sizeof(int32_t));
+  }
+  int32_t* dupHf = nullptr;
+  if (cfg.haar && numDup)
+    dupHf = ex.template alloc<int32_t>(size_t(N) * A);
+  ex.foreach(nLeaves, LeafFn{L, attrs, qpo, dupHf, A, cfg.haar});
+
+  //-- coarser stages, bottom-up
+  for (size_t i = 1; i < plan.size(); i++) {
+    Stage& F = stages.back();
+    Stage C = alloc_stage(ex, plan[i].level, plan[i].n, A, hasQp, true);
+    ex.compact(F.n, StageHead{F.key, F.level + 3}, StageEmit{F.key, C.key, C.first});
+    int32_t n32 = F.n;
+    ex.upload(C.first + C.n, &n32, sizeof(int32_t));
+    ex.foreach(C.n, MergeFn{F, C, A, cfg.haar});
+    stages.push_back(C);
+  }
+
+  //-- descent, coarse to fine
+  int qpLayer = 0;
+  if (hasStages) {
+    // zero-run look-back words: one per block of every stage, plus the
+    // initial state
+    int64_t totalBlocks = 1;
+    for (size_t i = 0; i + 1 < stages.size(); i++)
+      totalBlocks += stages[i + 1].n;
+    int* tz = nullptr;
+    const bool rdoq = forward && !cfg.haar;
+    if (rdoq) {
+      tz = ex.template alloc<int>(size_t(totalBlocks) + 1);
+      ex.zero(tz, (size_t(totalBlocks) + 1) * sizeof(int));
+      int init = tz_pack(kTzExit, 0);
+      ex.upload(tz, &init, sizeof(int));
+    }
+
+    int acLayer = -1;
+    int64_t blockBase = 0;
+    for (int si = int(stages.size()) - 1; si >= 0; si--) {
+      qpLayer = qpLayer + 1 < qs.num_layers ? qpLayer + 1 : qs.num_layers - 1;
+      acLayer++;
+      BlockFn fn;
+      fn.cfg = cfg;
+      fn.qt = qt;
+      fn.S = stages[si];
+      fn.coef = coef;
+      fn.coefStride = coefStride;
+      fn.qpLayer = qpLayer;
+      fn.acLayer = acLayer;
+      fn.tz = tz ? tz + blockBase : nullptr;
+      if (si == int(stages.size()) - 1) {
+        fn.P = Stage{};
+        fn.P.n = 0;
+        fn.coefBase = 0;
+        fn.predInLvl = 0;
+        fn.useFlags = 0;
+        ex.foreach(1, fn);
+        blockBase += 1;
+        continue;
+      }
+      fn.P = stages[si + 1];
+      fn.coefBase = fn.P.n;
+      fn.predInLvl = cfg.predictionEnabled;
+      // intra-stage ordering is needed for sub-node prediction (spatial
+      // dependencies) and for the encoder's zero-run counter
+      const bool deps = (cfg.predictionEnabled && cfg.subnode) || rdoq;
+      fn.useFlags = deps;
+      if (deps) {
+        ex.zero(fn.P.done, size_t(fn.P.n) * sizeof(int));
+        ex.ordered(fn.P.n, fn);
+      } else {
+        ex.foreach(fn.P.n, fn);
+      }
+      blockBase += fn.P.n;
+    }
+  }
+
+  //-- duplicates + write-back
+  TailFn tail;
+  tail.cfg = cfg;
+  tail.qt = qt;
+  tail.L = stages[0];
+  tail.attrsIn = attrs;
+  tail.dupHf = dupHf;
+  tail.attrsOut = attrs;
+  tail.coef = coef;
+  tail.coefStride = coefStride;
+  tail.coefBase = hasStages ? nLeaves : 0;
+  tail.qpLayer = qpLayer;
+  tail.hasStages = hasStages;
+  ex.foreach(nLeaves, tail);
+  if (forward && !hasStages) {
+    // all points coincide: the reference codes N-1 coefficients and no DC;
+    // the last slot of each component is defined as zero here
+    int32_t z = 0;
+    for (int k = 0; k < A; k++)
+      ex.upload(coef + k * coefStride + (N - 1), &z, sizeof(int32_t));
+  }
+  return PCCB200_OK;
+}
+
+}  // namespace pccb200

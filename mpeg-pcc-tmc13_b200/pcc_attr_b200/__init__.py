@@ -1,0 +1,218 @@
+"""ctypes binding of the C ABI in include/pcc_attr_b200.h (used by the tests
+and bench.py; the product itself is the C ABI + CUDA kernels).
+
+There is no CPU fallback: importing works anywhere, but every compute call
+raises if libpcc_attr_b200.so is missing or no sm_100 device is present."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libpcc_attr_b200.so")
+
+MAX_QP_LAYERS = 32
+MAX_AC_QP_LAYERS = 32
+
+
+class RahtParams(C.Structure):
+    """pccb200_raht_params <- pcc::RahtPredictionParams (tmc3/hls.h:439-466)"""
+    _fields_ = [
+        ("prediction_enabled", C.c_int32),
+        ("integer_haar", C.c_int32),
+        ("prediction_threshold0", C.c_int32),
+        ("prediction_threshold1", C.c_int32),
+        ("subnode_prediction_enabled", C.c_int32),
+        ("prediction_search_range", C.c_int32),
+        ("pred_weight_parent", C.c_int32 * 19),
+        ("pred_weight_child", C.c_int32 * 12),
+        ("raht_extension", C.c_int32),
+    ]
+
+
+class QpSet(C.Structure):
+    """pccb200_qpset <- pcc::QpSet (tmc3/quantization.h:123-137)"""
+    _fields_ = [
+        ("num_layers", C.c_int32),
+        ("layers", (C.c_int32 * 2) * MAX_QP_LAYERS),
+        ("max_qp", C.c_int32),
+        ("fixed_point_qp_offset", C.c_int32),
+        ("num_ac_coeff_qp_layers", C.c_int32),
+        ("ac_coeff_qps", ((C.c_int32 * 2) * 7) * MAX_AC_QP_LAYERS),
+    ]
+
+
+class Predictor(C.Structure):
+    _fields_ = [
+        ("neighbor_count", C.c_uint32),
+        ("predictor_index", C.c_uint32 * 3),
+        ("weight", C.c_uint32 * 3),
+    ]
+
+
+PREDICTOR_DTYPE = np.dtype([("neighbor_count", "<u4"), ("predictor_index", "<u4", 3),
+                            ("weight", "<u4", 3)])
+
+EXPORTS = [
+    "pccb200_raht_params_default", "pccb200_raht_set_prediction_weights",
+    "pccb200_abi_version", "pccb200_set_device", "pccb200_last_error",
+    "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
+    "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
+    "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
+    "pccb200_lift_forward", "pccb200_lift_inverse",
+]
+
+
+class PccB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PccB200Error(
+                f"{LIB_PATH} not found: build it with `make -C mpeg-pcc-tmc13_b200` "
+                "(or __graft_entry__.build()); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        l.pccb200_last_error.restype = C.c_char_p
+        l.pccb200_kernel_launch_count.restype = C.c_uint64
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PccB200Error(f"pccb200 status {rc}: {lib().pccb200_last_error().decode()}")
+
+
+def _p(a, t):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):  # torch CPU tensor (e.g. pinned)
+        return C.cast(a.data_ptr(), C.POINTER(t))
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def default_params():
+    p = RahtParams()
+    lib().pccb200_raht_params_default(C.byref(p))
+    return p
+
+
+def kernel_launch_count():
+    return int(lib().pccb200_kernel_launch_count())
+
+
+def set_device(i):
+    _check(lib().pccb200_set_device(C.c_int(i)))
+
+
+def morton_sort(xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    n = xyz.shape[0]
+    keys = np.empty(n, dtype=np.int64)
+    order = np.empty(n, dtype=np.int32)
+    _check(lib().pccb200_morton_sort(_p(xyz, C.c_int32), C.c_int32(n), _p(keys, C.c_int64),
+                                     _p(order, C.c_int32)))
+    return keys, order
+
+
+def raht_forward(params, qpset, morton, attrs, qpoffs=None):
+    """-> (reconstructed attrs [N,A], coefficients [A,N])"""
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    n, a = attrs.shape
+    morton = np.ascontiguousarray(morton, dtype=np.int64)
+    coeffs = np.empty((a, n), dtype=np.int32)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    _check(lib().pccb200_raht_forward(C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32),
+                                      _p(morton, C.c_int64), _p(attrs, C.c_int32),
+                                      C.c_int32(a), C.c_int32(n), _p(coeffs, C.c_int32)))
+    return attrs, coeffs
+
+
+def raht_inverse(params, qpset, morton, coeffs, qpoffs=None):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int32)
+    a, n = coeffs.shape
+    morton = np.ascontiguousarray(morton, dtype=np.int64)
+    attrs = np.empty((n, a), dtype=np.int32)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    _check(lib().pccb200_raht_inverse(C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32),
+                                      _p(morton, C.c_int64), _p(attrs, C.c_int32),
+                                      C.c_int32(a), C.c_int32(n), _p(coeffs, C.c_int32)))
+    return attrs
+
+
+def attr_raht_encode_into(params, qpset, xyz, attrs_inout, coeffs_out, bitdepth=8,
+                          qpoffs=None, slice_offsets=None):
+    """Zero-copy form used by bench.py: arrays may be numpy or (pinned) torch
+    CPU tensors; attrs_inout [N,A] int32 is overwritten with the clipped
+    reconstruction, coeffs_out [A,N] int32 receives the coefficients."""
+    n, a = attrs_inout.shape
+    if slice_offsets is None:
+        _check(lib().pccb200_attr_raht_encode(
+            C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32), _p(xyz, C.c_int32),
+            _p(attrs_inout, C.c_int32), C.c_int32(a), C.c_int32(n), C.c_int32(bitdepth),
+            _p(coeffs_out, C.c_int32)))
+    else:
+        so = np.ascontiguousarray(slice_offsets, dtype=np.int64)
+        _check(lib().pccb200_attr_raht_encode_slices(
+            C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32), _p(xyz, C.c_int32),
+            _p(attrs_inout, C.c_int32), C.c_int32(a), C.c_int32(bitdepth),
+            _p(so, C.c_int64), C.c_int32(len(so) - 1), _p(coeffs_out, C.c_int32)))
+
+
+def attr_raht_encode(params, qpset, xyz, attrs, bitdepth=8, qpoffs=None, slice_offsets=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    n, a = attrs.shape
+    coeffs = np.empty((a, n), dtype=np.int32)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    attr_raht_encode_into(params, qpset, xyz, attrs, coeffs, bitdepth, qpoffs, slice_offsets)
+    return attrs, coeffs
+
+
+def attr_raht_decode(params, qpset, xyz, coeffs, bitdepth=8, qpoffs=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int32)
+    a, n = coeffs.shape
+    attrs = np.empty((n, a), dtype=np.int32)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    _check(lib().pccb200_attr_raht_decode(
+        C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32), _p(xyz, C.c_int32),
+        _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n), C.c_int32(bitdepth),
+        _p(coeffs, C.c_int32)))
+    return attrs
+
+
+def quant_weights(preds, num_points_in_lod):
+    preds = np.ascontiguousarray(preds, dtype=PREDICTOR_DTYPE)
+    npl = np.ascontiguousarray(num_points_in_lod, dtype=np.uint32)
+    n = preds.shape[0]
+    qw = np.empty(n, dtype=np.uint64)
+    _check(lib().pccb200_quant_weights(C.cast(preds.ctypes.data, C.POINTER(Predictor)),
+                                       C.c_int32(n), _p(npl, C.c_uint32), C.c_int32(len(npl)),
+                                       _p(qw, C.c_uint64)))
+    return qw
+
+
+def lift(forward, preds, qw, num_points_in_lod, attrs):
+    preds = np.ascontiguousarray(preds, dtype=PREDICTOR_DTYPE)
+    npl = np.ascontiguousarray(num_points_in_lod, dtype=np.uint32)
+    qw = np.ascontiguousarray(qw, dtype=np.uint64)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int64).copy()
+    if attrs.ndim == 1:
+        attrs = attrs[:, None]
+    n, a = attrs.shape
+    fn = lib().pccb200_lift_forward if forward else lib().pccb200_lift_inverse
+    _check(fn(C.cast(preds.ctypes.data, C.POINTER(Predictor)), _p(qw, C.c_uint64), C.c_int32(n),
+              _p(npl, C.c_uint32), C.c_int32(len(npl)), _p(attrs, C.c_int64), C.c_int32(a)))
+    return attrs

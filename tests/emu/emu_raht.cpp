@@ -1,0 +1,24 @@
+// emu_raht.cpp — TEST INFRASTRUCTURE ONLY: the RAHT kernel bodies of the
+// product (raht_core.cuh / raht_pipeline.cuh) compiled for the host and run
+// as loops (see exec_host.h).  Built by tests/emu/Makefile into libemu.so.
+#include "exec_host.h"
+#include "raht_pipeline.cuh"
+
+extern "C" int
+emu_raht(int forward, const pccb200_raht_params* pp, const pccb200_qpset* qs,
+         const int32_t* qpo, const int64_t* morton, int32_t* attrs, int A,
+         int N, int32_t* coeffs)
+{
+  HostExec ex;
+  return pccb200::raht_run(ex, *pp, *qs, forward != 0, morton, attrs, qpo,
+                           coeffs, int64_t(N), A, N);
+}
+
+extern "C" uint32_t emu_isqrt(uint64_t x) { return pccb200::isqrt64(x); }
+extern "C" uint64_t emu_irsqrt(uint64_t x) { return pccb200::irsqrt64(x); }
+extern "C" int64_t emu_morton_addr(int32_t x, int32_t y, int32_t z) { return pccb200::morton_addr(x, y, z); }
+extern "C" uint64_t emu_morton3d_add(uint64_t a, uint64_t b) { return pccb200::morton3d_add(a, b); }
+extern "C" int64_t emu_quantize(int qp, int64_t x) { return pccb200::make_quantizer(qp).quantize(x); }
+extern "C" int64_t emu_scale(int qp, int64_t x) { return pccb200::make_quantizer(qp).scale(x); }
+extern "C" int64_t emu_fixed_mul(int64_t a, int64_t b) { return pccb200::fx_mul(a, b); }
+extern "C" int64_t emu_div_approx(int64_t a, uint64_t b, int32_t s) { return pccb200::div_approx(a, b, s); }

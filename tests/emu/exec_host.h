@@ -1,0 +1,52 @@
+// exec_host.h — TEST INFRASTRUCTURE ONLY.
+//
+// Host "executor" for the kernel bodies in mpeg-pcc-tmc13_b200/csrc: runs
+// every per-item functor as a plain in-order loop so that the kernels' logic
+// (stage planning, node construction, coefficient addressing, the dataflow
+// protocol) can be unit-tested in a container without a GPU.  It is never
+// linked into the product library; the product path has no CPU fallback.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct HostExec {
+  std::vector<void*> blocks;
+  ~HostExec()
+  {
+    for (void* p : blocks)
+      free(p);
+  }
+  template<class T>
+  T* alloc(size_t n)
+  {
+    void* p = malloc((n ? n : 1) * sizeof(T));
+    memset(p, 0xCD, (n ? n : 1) * sizeof(T));  // poison: catch reads of unset data
+    blocks.push_back(p);
+    return static_cast<T*>(p);
+  }
+  void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  void upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+  void download(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+  template<class F>
+  void foreach(int64_t n, const F& f)
+  {
+    for (int64_t i = 0; i < n; i++)
+      f(i);
+  }
+  template<class F>
+  void ordered(int64_t n, const F& f)
+  {
+    for (int64_t i = 0; i < n; i++)
+      f(i);
+  }
+  template<class P, class E>
+  void compact(int64_t n, const P& pred, const E& emit)
+  {
+    int64_t rank = 0;
+    for (int64_t i = 0; i < n; i++)
+      if (pred(i))
+        emit(rank++, i);
+  }
+};

@@ -331,3 +331,40 @@ def cloud_random(n, bits, seed, a=3, dup_frac=0.0, bitdepth=8):
         xyz[dst] = xyz[src]
     attrs = rng.integers(0, 1 << bitdepth, size=(n, a), dtype=np.int32)
     return xyz, attrs
+
+
+# --------------------------------------------------------------------------
+# host emulation of the product's kernel bodies (tests/emu) — CPU tests only
+
+_emu = None
+
+
+def load_emu():
+    global _emu
+    if _emu is None:
+        emu_dir = os.path.join(ROOT, "tests", "emu")
+        subprocess.check_call(["make", "-s", "-C", emu_dir])
+        lib = C.CDLL(os.path.join(emu_dir, "libemu.so"))
+        lib.emu_raht.restype = C.c_int
+        for nm, res, args in (
+            ("isqrt", C.c_uint32, [C.c_uint64]),
+            ("irsqrt", C.c_uint64, [C.c_uint64]),
+            ("morton_addr", C.c_int64, [C.c_int32] * 3),
+            ("morton3d_add", C.c_uint64, [C.c_uint64] * 2),
+            ("quantize", C.c_int64, [C.c_int, C.c_int64]),
+            ("scale", C.c_int64, [C.c_int, C.c_int64]),
+            ("fixed_mul", C.c_int64, [C.c_int64] * 2),
+            ("div_approx", C.c_int64, [C.c_int64, C.c_uint64, C.c_int32]),
+        ):
+            f = getattr(lib, "emu_" + nm)
+            f.restype = res
+            f.argtypes = args
+        _emu = lib
+    return _emu
+
+
+def emu_raht(forward, params, qpset, morton, attrs, coeffs=None, qpoffs=None):
+    a, c, r = _run_raht(load_emu().emu_raht, forward, params, qpset, morton,
+                        attrs, coeffs, qpoffs)
+    assert r == 0, r
+    return a, c
