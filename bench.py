@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py — attribute-transform throughput of the B200-native RAHT path.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): one ~1M-point synthetic LiDAR ring cloud
+(Ford_01-shaped, 64 lasers, seed 2 + rank), RGB + reflectance, octree-raht
+lossy-attrs CTC settings (qp 34, chroma offset -2, prediction + sub-node
+prediction on, search range 2500).  One step = the attribute coder's RAHT hot
+path over one frame: for colour (A=3) and for reflectance (A=1), Morton key +
+sort, gather, forward transform (RDOQ + quantisation + reconstruction), clip
+and write back.  Frames shard one per GPU (weak scaling, no data-path
+collective; NCCL only broadcasts the parameter PODs).
+
+Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in
+HBM (CUDA events on the library's stream); `e2e` = the same through the
+host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed
+region).  The oracle / compiled reference is only used for the reported
+`cpu_baseline` and for `--impl reference`."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc13_b200"))
+
+N_POINTS = 1_000_000
+QP = 34
+CHROMA_OFFSET = -2
+SEARCH_RANGE = 2500
+METRIC = "attribute-transform Mpoints/s (RAHT forward: Morton sort + transform, RGB + reflectance)"
+ALG_BYTES_PER_POINT = (16 + 12 * 3) + (16 + 12 * 1)  # 52 (RGB) + 28 (reflectance)
+
+
+def workload_config():
+    return {
+        "workload": "configs[1]: octree-raht lossy-attrs, ~1M-point synthetic LiDAR ring cloud "
+                    "(Ford_01-shaped), RGB + reflectance, single slice",
+        "points_per_frame": N_POINTS,
+        "attributes": "RGB (A=3) + reflectance (A=1), 8-bit",
+        "qp": QP,
+        "raht": "prediction + sub-node prediction, rahtExtension, RDOQ, search range 2500",
+        "frames_per_step_per_gpu": 1,
+        "parallelism": "one frame per GPU, no data-path collective",
+        "l2": "512 MiB written between steps (excluded from timing) to flush L2",
+    }
+
+
+def make_frame(seed):
+    from pcc_attr_b200.synth import cloud_lidar
+
+    xyz, rgb = cloud_lidar(N_POINTS, seed=seed, a=3)
+    rng = np.random.default_rng(seed + 1000)
+    # reflectance: range-dependent intensity + noise
+    r = np.linalg.norm(xyz.astype(np.float64), axis=1)
+    refl = np.clip(200.0 * np.exp(-r / (r.max() + 1)) + rng.integers(-6, 7, size=r.shape), 0, 255)
+    return xyz, rgb.astype(np.int32), np.rint(refl).astype(np.int32)[:, None]
+
+
+def make_pods(pb):
+    p = pb.default_params()
+    p.prediction_search_range = SEARCH_RANGE
+    q = pb.QpSet()
+    q.num_layers = 1
+    q.layers[0][0] = QP
+    q.layers[0][1] = CHROMA_OFFSET
+    q.max_qp = 51
+    q.fixed_point_qp_offset = 0
+    q.num_ac_coeff_qp_layers = 0
+    return p, q
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap,utilization.gpu")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mxv, util = float(f[0]), float(f[1]), float(f[6])
+            except ValueError:
+                continue
+            mx = mxv
+            if util > 0:
+                sm.append(clk)
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            sm = [float(x.split(",")[0]) for x in self.lines if x and x.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(self.lines)}
+
+
+# ---------------------------------------------------------------------------
+# reference / oracle on the host cores
+
+def load_cpu_impl():
+    """(callable, kind): the compiled unmodified reference if it travelled with
+    the snapshot (oracle/_ref), else the oracle port."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libtmc13_ref.so")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pcc_testlib as tl
+
+    if os.path.exists(ref):
+        lib = C.CDLL(ref)
+        lib.tmc13ref_attr_raht.restype = C.c_double
+
+        def run(params, qpset, xyz, attrs):
+            a = attrs.copy()
+            coef = np.zeros((a.shape[1], a.shape[0]), dtype=np.int32)
+            lib.tmc13ref_attr_raht(
+                C.c_int(1), C.byref(params), C.byref(qpset), None,
+                xyz.ctypes.data_as(C.POINTER(C.c_int32)), a.ctypes.data_as(C.POINTER(C.c_int32)),
+                C.c_int(a.shape[1]), C.c_int(a.shape[0]), C.c_int(8),
+                coef.ctypes.data_as(C.POINTER(C.c_int32)))
+            return a, coef
+
+        return run, "reference"
+
+    def run(params, qpset, xyz, attrs):
+        mort, a_s, order = tl.sort_cloud(xyz, attrs)
+        rec, coef = tl.oracle_raht(1, params, qpset, mort, a_s)
+        out = np.empty_like(rec)
+        out[order] = np.clip(rec, 0, 255)
+        return out, coef
+
+    return run, "port"
+
+
+def cpu_frame_seconds(run, params, qpset, frame):
+    xyz, rgb, refl = frame
+    t0 = time.perf_counter()
+    run(params, qpset, xyz, rgb)
+    run(params, qpset, xyz, refl)
+    return time.perf_counter() - t0
+
+
+def host_cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pcc_testlib as tl
+
+    run, kind = load_cpu_impl()
+    params = tl.make_params(search_range=SEARCH_RANGE)
+    qpset = tl.make_qpset(qp=QP, chroma_offset=CHROMA_OFFSET)
+    frame = make_frame(2)
+    cores = min(os.cpu_count() or 1, 64)
+    if kind == "port":
+        cores = 1  # the oracle port is driven through numpy here: one thread
+
+    def one_step():
+        ts = [threading.Thread(target=cpu_frame_seconds, args=(run, params, qpset, frame))
+              for _ in range(cores)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    total = 0.0
+    for _ in range(args.steps):
+        total += one_step()
+    n = frame[0].shape[0]
+    value = cores * n * args.steps / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpoints/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {
+            "value": value, "unit": "Mpoints/s", "cores": cores, "kind": kind,
+            "sample": f"each step: {cores} independent copies of the 1 frame workload "
+                      f"({n} points, RGB + reflectance), one per host thread "
+                      f"(the reference itself is single-threaded); host: {host_cpu_model()}"},
+        "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pcc_attr_b200 as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pb.lib()
+    pb.set_device(local)
+
+    # parameter PODs: rank 0 owns them, NCCL broadcasts the bytes
+    params, qpset = make_pods(pb)
+    if distributed:
+        blob = bytes(params) + bytes(qpset)
+        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        params = pb.RahtParams.from_buffer_copy(raw[:C.sizeof(pb.RahtParams)])
+        qpset = pb.QpSet.from_buffer_copy(raw[C.sizeof(pb.RahtParams):])
+
+    frame = make_frame(2 + rank)
+    xyz, rgb, refl = frame
+    n = xyz.shape[0]
+
+    # device-resident inputs
+    d_xyz = torch.from_numpy(xyz).to(dev)
+    d_rgb0 = torch.from_numpy(rgb).to(dev)
+    d_refl0 = torch.from_numpy(refl).to(dev)
+    d_rgb = torch.empty_like(d_rgb0)
+    d_refl = torch.empty_like(d_refl0)
+    d_crgb = torch.empty((3, n), dtype=torch.int32, device=dev)
+    d_crefl = torch.empty((1, n), dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    lib_stream = torch.cuda.ExternalStream(pb.stream_handle(), device=dev)
+
+    def step_device():
+        pb.attr_raht_encode_dev(params, qpset, d_xyz.data_ptr(), d_rgb.data_ptr(),
+                                d_crgb.data_ptr(), n, 3)
+        pb.attr_raht_encode_dev(params, qpset, d_xyz.data_ptr(), d_refl.data_ptr(),
+                                d_crefl.data_ptr(), n, 1)
+
+    def prepare():
+        flush.fill_(1)
+        d_rgb.copy_(d_rgb0)
+        d_refl.copy_(d_refl0)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        prepare()
+        step_device()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = pb.kernel_launch_count()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        prepare()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(lib_stream)
+        step_device()
+        e1.record(lib_stream)
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    launches = pb.kernel_launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-phase kernel time (CUDA events around every launch), a few extra steps
+    pb.profile_reset()
+    pb.profile_enable(True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        prepare()
+        step_device()
+    pb.profile_enable(False)
+    prof = pb.profile_read()
+
+    # end to end through the host-pointer C ABI, pinned host buffers
+    h_xyz = torch.from_numpy(xyz).pin_memory()
+    h_rgb0 = torch.from_numpy(rgb).pin_memory()
+    h_refl0 = torch.from_numpy(refl).pin_memory()
+    h_rgb = torch.empty_like(h_rgb0).pin_memory()
+    h_refl = torch.empty_like(h_refl0).pin_memory()
+    h_crgb = torch.empty((3, n), dtype=torch.int32).pin_memory()
+    h_crefl = torch.empty((1, n), dtype=torch.int32).pin_memory()
+
+    def step_host():
+        pb.attr_raht_encode_into(params, qpset, h_xyz, h_rgb, h_crgb)
+        pb.attr_raht_encode_into(params, qpset, h_xyz, h_refl, h_crefl)
+
+    for _ in range(2):
+        h_rgb.copy_(h_rgb0)
+        h_refl.copy_(h_refl0)
+        step_host()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        h_rgb.copy_(h_rgb0)
+        h_refl.copy_(h_refl0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_host()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    h2d = 2 * xyz.nbytes + rgb.nbytes + refl.nbytes
+    d2h = 2 * (rgb.nbytes + refl.nbytes)
+    e2e_loss = int(h_crgb.numpy().astype(np.int64).__abs__().sum())  # result read on the host
+
+    if distributed:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        blk_ms, blk_launches = prof["block_transform"]
+        blk_ms_per_step = blk_ms / prof_steps
+        achieved = ALG_BYTES_PER_POINT * n / (blk_ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("block_transform_dram_bytes_per_step")
+        line = {
+            "metric": METRIC,
+            "value": world * n * args.steps / (total_ms * 1e-3) / 1e6,
+            "unit": "Mpoints/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": workload_config(),
+            "e2e": {"value": world * n * args.steps / e2e_s / 1e6, "unit": "Mpoints/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "result_checksum": e2e_loss},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_ordered<BlockFn> (top-down block transform, all stages)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": ALG_BYTES_PER_POINT * n,
+                "kernel_ms_per_step": blk_ms_per_step,
+                "kernel_launches_per_step": blk_launches / prof_steps,
+                "note": "dependency/latency bound integer transform; see DESIGN.md"},
+            "phase_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
+        }
+        # reported CPU baseline: single N=1 run only (bounded: one frame)
+        if world == 1 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import pcc_testlib as tl
+
+            run, kind = load_cpu_impl()
+            secs = cpu_frame_seconds(run, tl.make_params(search_range=SEARCH_RANGE),
+                                     tl.make_qpset(qp=QP, chroma_offset=CHROMA_OFFSET), frame)
+            line["cpu_baseline"] = {
+                "value": n / secs / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": kind,
+                "sample": f"1 frame of the same workload ({n} points, RGB + reflectance), "
+                          f"{secs:.2f} s on one host core; host: {host_cpu_model()}"}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

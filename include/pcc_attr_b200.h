@@ -168,6 +168,45 @@ int pccb200_attr_raht_encode_slices(const pccb200_raht_params* params,
                                     const int64_t* slice_offsets,
                                     int32_t num_slices, int32_t* coeffs_out);
 
+/* Device-resident variants (inputs and outputs already in HBM) ------------- */
+
+/* The CUDA stream (cudaStream_t) every call of this library is issued on, so
+ * that a caller can order its own work or record events against it. */
+void* pccb200_stream(void);
+
+/* As pccb200_attr_raht_encode_slices / a decode counterpart, but every array
+ * pointer is a DEVICE pointer on the selected device; slice_offsets stays a
+ * host array.  Work is issued on pccb200_stream() and complete on return. */
+int pccb200_attr_raht_encode_slices_dev(const pccb200_raht_params* params,
+                                        const pccb200_qpset* qpset,
+                                        const int32_t* d_point_qp_offsets,
+                                        const int32_t* d_xyz,
+                                        int32_t* d_attrs_inout, int32_t num_attrs,
+                                        int32_t bitdepth,
+                                        const int64_t* slice_offsets,
+                                        int32_t num_slices,
+                                        int32_t* d_coeffs_out);
+int pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
+                                        const pccb200_qpset* qpset,
+                                        const int32_t* d_point_qp_offsets,
+                                        const int32_t* d_xyz, int32_t* d_attrs_out,
+                                        int32_t num_attrs, int32_t bitdepth,
+                                        const int64_t* slice_offsets,
+                                        int32_t num_slices,
+                                        const int32_t* d_coeffs_in);
+
+/* Per-phase device timing (CUDA events around every kernel launch on
+ * pccb200_stream()).  Phases: 0 Morton keys + radix sort, 1 tree build
+ * (histogram, compaction, leaf / merge kernels), 2 block transform (the
+ * top-down dataflow kernels), 3 duplicate tail + write-back, 4 gather /
+ * scatter / clip, 5 lifting passes.  pccb200_profile_read returns the
+ * accumulated milliseconds and launch counts since the last reset. */
+#define PCCB200_NUM_PHASES 6
+void pccb200_profile_enable(int enable);
+void pccb200_profile_reset(void);
+void pccb200_profile_read(double ms_out[PCCB200_NUM_PHASES],
+                          uint64_t launches_out[PCCB200_NUM_PHASES]);
+
 /* Lifting transform ------------------------------------------------------- */
 
 /* Flattened pcc::PCCPredictor as consumed by the lifting passes

@@ -15,6 +15,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "pcc_attr_b200.h"
 #include <stdio.h>
 
 #include <atomic>
@@ -251,11 +253,77 @@ k_tile_emit(P pred, E emit, int64_t n, const int* tileOffset)
 
 //----------------------------------------------------------------------------
 
+// optional per-phase timing: one event pair per launch, resolved after the
+// call's final synchronisation
+struct Profiler {
+  bool enabled = false;
+  double ms[PCCB200_NUM_PHASES] = {};
+  uint64_t launches[PCCB200_NUM_PHASES] = {};
+  struct Pending {
+    int phase;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+
+  cudaEvent_t get()
+  {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    PCC_CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+  }
+  void resolve()
+  {
+    for (auto& p : pending) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) {
+        ms[p.phase] += t;
+        launches[p.phase]++;
+      }
+      pool.push_back(p.a);
+      pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+};
+
+enum Phase { kPhaseSort = 0, kPhaseTree, kPhaseBlock, kPhaseTail, kPhaseGather, kPhaseLift };
+
 struct DeviceExec {
   cudaStream_t stream = nullptr;
   Arena* arena = nullptr;
   int numSMs = 148;
   unsigned long long* ticket = nullptr;  // device word for ordered launches
+  Profiler* prof = nullptr;
+  int curPhase = 0;
+
+  void phase(int p) { curPhase = p; }
+
+  // brackets one launch (or a short group of launches) with events
+  struct Scope {
+    DeviceExec& ex;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit Scope(DeviceExec& e) : ex(e)
+    {
+      if (ex.prof && ex.prof->enabled) {
+        a = ex.prof->get();
+        b = ex.prof->get();
+        cudaEventRecord(a, ex.stream);
+      }
+    }
+    ~Scope()
+    {
+      if (a) {
+        cudaEventRecord(b, ex.stream);
+        ex.prof->pending.push_back({ex.curPhase, a, b});
+      }
+    }
+  };
 
   template<class T>
   T* alloc(size_t n)
@@ -291,6 +359,7 @@ struct DeviceExec {
     int64_t cap = int64_t(numSMs) * 16;
     if (blocks > cap)
       blocks = cap;
+    Scope sc(*this);
     k_foreach<F><<<unsigned(blocks), 256, 0, stream>>>(f, n);
     g_launchCount++;
     PCC_CUDA_CHECK(cudaGetLastError());
@@ -311,6 +380,7 @@ struct DeviceExec {
     int64_t cap = int64_t(numSMs) * perSM;
     if (blocks > cap)
       blocks = cap;
+    Scope sc(*this);
     k_ordered<F><<<unsigned(blocks), kOrderedThreads, 0, stream>>>(f, n, ticket);
     g_launchCount++;
     PCC_CUDA_CHECK(cudaGetLastError());
@@ -323,6 +393,7 @@ struct DeviceExec {
       return;
     int numTiles = int((n + kTile - 1) / kTile);
     int* tiles = alloc<int>(numTiles);
+    Scope sc(*this);
     k_tile_count<P><<<numTiles, kTileThreads, 0, stream>>>(pred, n, tiles);
     k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, numTiles);
     k_tile_emit<P, E><<<numTiles, kTileThreads, 0, stream>>>(pred, emit, n, tiles);

@@ -158,6 +158,7 @@ int
 run_quant_weights(Exec& ex, const pccb200_predictor* preds, int64_t n,
                   const uint32_t* numPointsInLod, int lodCount, uint64_t* qw)
 {
+  ex.phase(5);
   ex.foreach(n, FillU64Fn{qw, uint64_t(1) << 8});
   int* dFlags = ex.template alloc<int>(size_t(lodCount) + 1);
   ex.zero(dFlags, (size_t(lodCount) + 1) * sizeof(int));
@@ -192,6 +193,7 @@ run_lift(Exec& ex, bool forward, const pccb200_predictor* preds, const uint64_t*
 {
   if (lodCount < 1 || int64_t(numPointsInLod[lodCount - 1]) != n)
     return PCCB200_ERR_INVALID_ARG;
+  ex.phase(5);
   // the lifting passes require strictly-coarser references
   int* dFlag = ex.template alloc<int>(1);
   ex.zero(dFlag, sizeof(int));

@@ -232,6 +232,7 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
 {
   if (n <= 0)
     return;
+  ex.phase(kPhaseSort);
   cudaStream_t st = ex.stream;
   int64_t* keysTmp = ex.alloc<int64_t>(n);
   int32_t* valsTmp = ex.alloc<int32_t>(n);
@@ -240,7 +241,10 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
 
   // the pass count is not known yet, so generate into the "A" buffers and
   // let the parity of the pass count decide where the result lands
-  k_morton_keys<<<grid_for(n, ex.numSMs), 256, 0, st>>>(dXyz, n, keysOut, orderOut, dOr);
+  {
+    DeviceExec::Scope sc(ex);
+    k_morton_keys<<<grid_for(n, ex.numSMs), 256, 0, st>>>(dXyz, n, keysOut, orderOut, dOr);
+  }
   g_launchCount++;
   unsigned long long hOr = 0;
   ex.download(&hOr, dOr, sizeof(hOr));
@@ -261,6 +265,7 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
   int32_t* vout = valsTmp;
   for (int p = 0; p < passes; p++) {
     const int shift = 8 * p;
+    DeviceExec::Scope sc(ex);
     k_radix_hist<<<numTiles, kSortThreads, 0, st>>>(kin, n, shift, numTiles, hist);
     k_scan_sum<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
     k_scan_tiles<<<1, 1024, 0, st>>>(tileSums, scanTiles);

@@ -32,6 +32,7 @@ struct Context {
   Arena arena;
   unsigned long long* ticket = nullptr;
   int numSMs = 0;
+  Profiler prof;
 };
 
 Context&
@@ -92,6 +93,7 @@ make_exec(Context& c)
   ex.arena = &c.arena;
   ex.numSMs = c.numSMs;
   ex.ticket = c.ticket;
+  ex.prof = &c.prof;
   return ex;
 }
 
@@ -129,6 +131,7 @@ with_device(Body body)
     DeviceExec ex = make_exec(c);
     rc = body(ex);
     PCC_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.prof.resolve();
     if (rc != PCCB200_OK && t_lastError.empty())
       t_lastError = "invalid argument";
     return rc;
@@ -165,62 +168,111 @@ raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset
   });
 }
 
+// all array pointers are device pointers; sliceOffsets is a host array
+int
+attr_raht_core(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
+               const pccb200_qpset* qpset, const int32_t* dQpoIn, const int32_t* dXyz,
+               const int32_t* dAttrsIn, int32_t* dAttrsOut, int A, int bitdepth,
+               const int64_t* sliceOffsets, int numSlices, int32_t* dCoef)
+{
+  const int64_t total = sliceOffsets[numSlices];
+  int64_t* dKeys = ex.alloc<int64_t>(size_t(total));
+  int32_t* dOrder = ex.alloc<int32_t>(size_t(total));
+  int32_t* dAttrs = ex.alloc<int32_t>(size_t(total) * A);
+  int32_t* dQpo = dQpoIn ? ex.alloc<int32_t>(size_t(total) * 2) : nullptr;
+  const int32_t clipMax = (1 << bitdepth) - 1;
+  for (int s = 0; s < numSlices; s++) {
+    const int64_t o = sliceOffsets[s];
+    const int n = int(sliceOffsets[s + 1] - o);
+    device_morton_sort(ex, dXyz + 3 * o, n, dKeys + o, dOrder + o);
+    const unsigned g = grid_for(n, ex.numSMs);
+    ex.phase(kPhaseGather);
+    if (forward) {
+      DeviceExec::Scope sc(ex);
+      k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dAttrsIn + o * A, dOrder + o, n, A,
+                                                       dAttrs + o * A);
+      g_launchCount++;
+    }
+    if (dQpoIn) {
+      DeviceExec::Scope sc(ex);
+      k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dQpoIn + 2 * o, dOrder + o, n, 2,
+                                                       dQpo + 2 * o);
+      g_launchCount++;
+    }
+    int rc = raht_run(ex, *params, *qpset, forward, dKeys + o, dAttrs + o * A,
+                      dQpoIn ? dQpo + 2 * o : nullptr, dCoef + o, total, A, n);
+    if (rc != PCCB200_OK)
+      return fail(rc, "invalid parameters");
+    ex.phase(kPhaseGather);
+    {
+      DeviceExec::Scope sc(ex);
+      k_scatter_rows_clip<<<g, 256, 0, ex.stream>>>(dAttrs + o * A, dOrder + o, n, A, clipMax,
+                                                    dAttrsOut + o * A);
+      g_launchCount++;
+    }
+  }
+  PCC_CUDA_CHECK(cudaGetLastError());
+  return PCCB200_OK;
+}
+
+int
+check_slices(const void* params, const void* qpset, const void* xyz, const void* attrs,
+             const void* coeffs, int A, int bitdepth, const int64_t* sliceOffsets,
+             int numSlices)
+{
+  if (!params || !qpset || !xyz || !attrs || !coeffs || !sliceOffsets || numSlices <= 0
+      || A < 1 || A > 3 || bitdepth < 1 || bitdepth > 16)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  for (int s = 0; s < numSlices; s++) {
+    int64_t len = sliceOffsets[s + 1] - sliceOffsets[s];
+    if (len <= 0 || len > INT32_MAX)
+      return fail(PCCB200_ERR_INVALID_ARG, "empty or oversized slice");
+  }
+  return PCCB200_OK;
+}
+
 int
 attr_raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset* qpset,
                  const int32_t* qpo, const int32_t* xyz, int32_t* attrs, int A,
                  int bitdepth, const int64_t* sliceOffsets, int numSlices,
                  int32_t* coeffs)
 {
-  if (!params || !qpset || !xyz || !attrs || !coeffs || !sliceOffsets || numSlices <= 0
-      || A < 1 || A > 3 || bitdepth < 1 || bitdepth > 16)
-    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  int rc = check_slices(params, qpset, xyz, attrs, coeffs, A, bitdepth, sliceOffsets, numSlices);
+  if (rc != PCCB200_OK)
+    return rc;
   const int64_t total = sliceOffsets[numSlices];
-  for (int s = 0; s < numSlices; s++) {
-    int64_t len = sliceOffsets[s + 1] - sliceOffsets[s];
-    if (len <= 0 || len > INT32_MAX)
-      return fail(PCCB200_ERR_INVALID_ARG, "empty or oversized slice");
-  }
   return with_device([&](DeviceExec& ex) -> int {
     int32_t* dXyz = to_device(ex, xyz, size_t(total) * 3);
-    int32_t* dAttrsIn = forward ? to_device(ex, attrs, size_t(total) * A)
-                                : ex.alloc<int32_t>(size_t(total) * A);
+    int32_t* dAttrsIn = forward ? to_device(ex, attrs, size_t(total) * A) : nullptr;
     int32_t* dQpoIn = qpo ? to_device(ex, qpo, size_t(total) * 2) : nullptr;
     int32_t* dCoef = forward ? ex.alloc<int32_t>(size_t(total) * A)
                              : to_device(ex, coeffs, size_t(total) * A);
-    int64_t* dKeys = ex.alloc<int64_t>(size_t(total));
-    int32_t* dOrder = ex.alloc<int32_t>(size_t(total));
-    int32_t* dAttrs = ex.alloc<int32_t>(size_t(total) * A);
-    int32_t* dQpo = qpo ? ex.alloc<int32_t>(size_t(total) * 2) : nullptr;
     int32_t* dOut = ex.alloc<int32_t>(size_t(total) * A);
-    const int32_t clipMax = (1 << bitdepth) - 1;
-    for (int s = 0; s < numSlices; s++) {
-      const int64_t o = sliceOffsets[s];
-      const int n = int(sliceOffsets[s + 1] - o);
-      device_morton_sort(ex, dXyz + 3 * o, n, dKeys + o, dOrder + o);
-      const unsigned g = grid_for(n, ex.numSMs);
-      if (forward) {
-        k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dAttrsIn + o * A, dOrder + o, n, A,
-                                                         dAttrs + o * A);
-        g_launchCount++;
-      }
-      if (qpo) {
-        k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dQpoIn + 2 * o, dOrder + o, n, 2,
-                                                         dQpo + 2 * o);
-        g_launchCount++;
-      }
-      int rc = raht_run(ex, *params, *qpset, forward, dKeys + o, dAttrs + o * A,
-                        qpo ? dQpo + 2 * o : nullptr, dCoef + o, total, A, n);
-      if (rc != PCCB200_OK)
-        return fail(rc, "invalid parameters");
-      k_scatter_rows_clip<<<g, 256, 0, ex.stream>>>(dAttrs + o * A, dOrder + o, n, A, clipMax,
-                                                    dOut + o * A);
-      g_launchCount++;
-    }
-    PCC_CUDA_CHECK(cudaGetLastError());
+    int rc2 = attr_raht_core(ex, forward, params, qpset, dQpoIn, dXyz, dAttrsIn, dOut, A,
+                             bitdepth, sliceOffsets, numSlices, dCoef);
+    if (rc2 != PCCB200_OK)
+      return rc2;
     to_host(ex, attrs, dOut, size_t(total) * A);
     if (forward)
       to_host(ex, coeffs, dCoef, size_t(total) * A);
     return PCCB200_OK;
+  });
+}
+
+int
+attr_raht_common_dev(bool forward, const pccb200_raht_params* params,
+                     const pccb200_qpset* qpset, const int32_t* dQpo, const int32_t* dXyz,
+                     int32_t* dAttrs, int A, int bitdepth, const int64_t* sliceOffsets,
+                     int numSlices, int32_t* dCoef)
+{
+  int rc = check_slices(params, qpset, dXyz, dAttrs, dCoef, A, bitdepth, sliceOffsets, numSlices);
+  if (rc != PCCB200_OK)
+    return rc;
+  return with_device([&](DeviceExec& ex) -> int {
+    // in-place on the caller's attribute buffer: the gather reads it before
+    // the final scatter overwrites it
+    return attr_raht_core(ex, forward, params, qpset, dQpo, dXyz, dAttrs, dAttrs, A, bitdepth,
+                          sliceOffsets, numSlices, dCoef);
   });
 }
 
@@ -360,6 +412,71 @@ pccb200_attr_raht_encode_slices(const pccb200_raht_params* params, const pccb200
 {
   return attr_raht_common(true, params, qpset, point_qp_offsets, xyz, attrs_inout, num_attrs,
                           bitdepth, slice_offsets, num_slices, coeffs_out);
+}
+
+int
+pccb200_attr_raht_encode_slices_dev(const pccb200_raht_params* params,
+                                    const pccb200_qpset* qpset,
+                                    const int32_t* d_point_qp_offsets, const int32_t* d_xyz,
+                                    int32_t* d_attrs_inout, int32_t num_attrs, int32_t bitdepth,
+                                    const int64_t* slice_offsets, int32_t num_slices,
+                                    int32_t* d_coeffs_out)
+{
+  return attr_raht_common_dev(true, params, qpset, d_point_qp_offsets, d_xyz, d_attrs_inout,
+                              num_attrs, bitdepth, slice_offsets, num_slices, d_coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
+                                    const pccb200_qpset* qpset,
+                                    const int32_t* d_point_qp_offsets, const int32_t* d_xyz,
+                                    int32_t* d_attrs_out, int32_t num_attrs, int32_t bitdepth,
+                                    const int64_t* slice_offsets, int32_t num_slices,
+                                    const int32_t* d_coeffs_in)
+{
+  return attr_raht_common_dev(false, params, qpset, d_point_qp_offsets, d_xyz, d_attrs_out,
+                              num_attrs, bitdepth, slice_offsets, num_slices,
+                              const_cast<int32_t*>(d_coeffs_in));
+}
+
+void*
+pccb200_stream(void)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (ensure_ready(c) != PCCB200_OK)
+    return nullptr;
+  return c.stream;
+}
+
+void
+pccb200_profile_enable(int enable)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.prof.enabled = enable != 0;
+}
+
+void
+pccb200_profile_reset(void)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
+    c.prof.ms[i] = 0;
+    c.prof.launches[i] = 0;
+  }
+}
+
+void
+pccb200_profile_read(double ms_out[PCCB200_NUM_PHASES], uint64_t launches_out[PCCB200_NUM_PHASES])
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
+    ms_out[i] = c.prof.ms[i];
+    launches_out[i] = c.prof.launches[i];
+  }
 }
 
 int

@@ -5,6 +5,7 @@
 //
 // Executor concept:
 //   T*   alloc<T>(size_t n)                 workspace memory (uninitialised)
+//   void phase(int p)                        tag following launches (profiling)
 //   void zero(void* p, size_t bytes)
 //   void upload(void* dst, const void* src, size_t bytes)      host -> exec
 //   void download(void* dst, const void* src, size_t bytes)    exec -> host, synchronous
@@ -142,6 +143,7 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   QpTables* qt = ex.template alloc<QpTables>(1);
   ex.upload(qt, &hostQt, sizeof(QpTables));
 
+  ex.phase(1);  // tree build
   if (N == 1) {
     ex.foreach(1, SinglePointFn{cfg, qt, qpo, attrs, coef, coefStride});
     return PCCB200_OK;
@@ -187,6 +189,7 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   }
 
   //-- descent, coarse to fine
+  ex.phase(2);  // block transform
   int qpLayer = 0;
   if (hasStages) {
     // zero-run look-back words: one per block of every stage, plus the
@@ -245,6 +248,7 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   }
 
   //-- duplicates + write-back
+  ex.phase(3);
   TailFn tail;
   tail.cfg = cfg;
   tail.qt = qt;

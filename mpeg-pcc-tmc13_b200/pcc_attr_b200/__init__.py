@@ -59,8 +59,12 @@ EXPORTS = [
     "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
     "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
     "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
-    "pccb200_lift_forward", "pccb200_lift_inverse",
+    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_stream",
+    "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
+    "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
 ]
+NUM_PHASES = 6
+PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
 
 
 class PccB200Error(RuntimeError):
@@ -81,6 +85,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.pccb200_last_error.restype = C.c_char_p
         l.pccb200_kernel_launch_count.restype = C.c_uint64
+        l.pccb200_stream.restype = C.c_void_p
         _lib = l
     return _lib
 
@@ -216,3 +221,48 @@ def lift(forward, preds, qw, num_points_in_lod, attrs):
     _check(fn(C.cast(preds.ctypes.data, C.POINTER(Predictor)), _p(qw, C.c_uint64), C.c_int32(n),
               _p(npl, C.c_uint32), C.c_int32(len(npl)), _p(attrs, C.c_int64), C.c_int32(a)))
     return attrs
+
+
+# ---- device-resident entry points (pointers are raw device addresses) ------
+
+def stream_handle():
+    """cudaStream_t of the library, as an int (for torch.cuda.ExternalStream)."""
+    h = lib().pccb200_stream()
+    if not h:
+        raise PccB200Error(lib().pccb200_last_error().decode())
+    return int(h)
+
+
+def attr_raht_encode_dev(params, qpset, d_xyz, d_attrs_inout, d_coeffs, n, a, bitdepth=8,
+                         d_qpoffs=0, slice_offsets=None):
+    so = np.ascontiguousarray(slice_offsets if slice_offsets is not None else [0, n],
+                              dtype=np.int64)
+    _check(lib().pccb200_attr_raht_encode_slices_dev(
+        C.byref(params), C.byref(qpset), C.c_void_p(d_qpoffs or None), C.c_void_p(d_xyz),
+        C.c_void_p(d_attrs_inout), C.c_int32(a), C.c_int32(bitdepth), _p(so, C.c_int64),
+        C.c_int32(len(so) - 1), C.c_void_p(d_coeffs)))
+
+
+def attr_raht_decode_dev(params, qpset, d_xyz, d_attrs_out, d_coeffs, n, a, bitdepth=8,
+                         d_qpoffs=0, slice_offsets=None):
+    so = np.ascontiguousarray(slice_offsets if slice_offsets is not None else [0, n],
+                              dtype=np.int64)
+    _check(lib().pccb200_attr_raht_decode_slices_dev(
+        C.byref(params), C.byref(qpset), C.c_void_p(d_qpoffs or None), C.c_void_p(d_xyz),
+        C.c_void_p(d_attrs_out), C.c_int32(a), C.c_int32(bitdepth), _p(so, C.c_int64),
+        C.c_int32(len(so) - 1), C.c_void_p(d_coeffs)))
+
+
+def profile_enable(on):
+    lib().pccb200_profile_enable(C.c_int(1 if on else 0))
+
+
+def profile_reset():
+    lib().pccb200_profile_reset()
+
+
+def profile_read():
+    ms = (C.c_double * NUM_PHASES)()
+    ln = (C.c_uint64 * NUM_PHASES)()
+    lib().pccb200_profile_read(ms, ln)
+    return {PHASE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_PHASES)}

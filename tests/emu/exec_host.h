@@ -26,6 +26,7 @@ struct HostExec {
     blocks.push_back(p);
     return static_cast<T*>(p);
   }
+  void phase(int) {}
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
   void upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
   void download(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }

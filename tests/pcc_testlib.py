@@ -231,106 +231,11 @@ def ref_morton_sort(xyz):
     return keys, order
 
 
-def np_morton(xyz):
-    """Vectorised Morton code (x->bit2, y->bit1, z->bit0), 21 bits/axis."""
-    xyz = np.asarray(xyz, dtype=np.int64)
-    out = np.zeros(xyz.shape[0], dtype=np.int64)
-    for b in range(21):
-        out |= ((xyz[:, 0] >> b) & 1) << (3 * b + 2)
-        out |= ((xyz[:, 1] >> b) & 1) << (3 * b + 1)
-        out |= ((xyz[:, 2] >> b) & 1) << (3 * b)
-    return out
+import sys as _sys
 
-
-def sort_cloud(xyz, attrs):
-    """Stable Morton sort of a cloud; returns (morton, attrs_sorted, order)."""
-    keys = np_morton(xyz)
-    order = np.argsort(keys, kind="stable")
-    return keys[order], np.ascontiguousarray(attrs[order]), order
-
-
-# --------------------------------------------------------------------------
-# synthetic clouds (SURVEY.md 8d)
-
-def _smooth_attr(xyz, rng, a, noise=8, bitdepth=8):
-    x = xyz.astype(np.float64)
-    span = max(1.0, float(x.max()))
-    base = np.stack([
-        128 + 90 * np.sin(6.0 * x[:, 0] / span + 0.3) * np.cos(4.0 * x[:, 1] / span),
-        128 + 80 * np.cos(5.0 * x[:, 1] / span + 1.1) * np.sin(3.0 * x[:, 2] / span),
-        128 + 70 * np.sin(7.0 * (x[:, 0] + x[:, 2]) / span),
-    ], axis=1)[:, :a]
-    v = base * ((1 << bitdepth) / 256.0) + rng.integers(-noise, noise + 1, size=(xyz.shape[0], a))
-    return np.clip(np.rint(v), 0, (1 << bitdepth) - 1).astype(np.int32)
-
-
-def cloud_cube(n=100000, side=47, offset=8, seed=1, a=3):
-    """Config 1: first n voxels (Morton order) of a filled side^3 cube."""
-    rng = np.random.default_rng(seed)
-    g = np.arange(side, dtype=np.int32) + offset
-    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
-    keys = np_morton(xyz)
-    xyz = xyz[np.argsort(keys, kind="stable")][:n]
-    xyz = xyz[rng.permutation(xyz.shape[0])]
-    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
-
-
-def cloud_shell(n=100000, bits=10, seed=3, a=3, dups=False):
-    """Sphere-shell surface voxelised to `bits` bits (configs 3-5 shape)."""
-    rng = np.random.default_rng(seed)
-    m = int(n * (1.6 if not dups else 1.0))
-    v = rng.normal(size=(m, 3))
-    v /= np.linalg.norm(v, axis=1, keepdims=True)
-    r = (1 << bits) * 0.45 * (1 + 0.1 * np.sin(5 * v[:, 0]) * np.cos(3 * v[:, 1]))
-    xyz = np.clip(np.rint(v * r[:, None] + (1 << bits) / 2), 0, (1 << bits) - 1).astype(np.int32)
-    if not dups:
-        xyz = np.unique(xyz, axis=0)
-        xyz = xyz[rng.permutation(xyz.shape[0])]
-    xyz = xyz[:n]
-    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
-
-
-def cloud_lidar(n=1000000, seed=2, a=3, scale=0.03125, lasers=64):
-    """Config 2: Ford-shaped spinning-LiDAR ring cloud, 1 mm grid scaled by
-    `scale` (positionQuantizationScale), duplicates merged."""
-    rng = np.random.default_rng(seed)
-    az_steps = (n * 115 // 100) // lasers + 1
-    theta = np.deg2rad(np.linspace(-24.8, 2.0, lasers))
-    az = np.linspace(0, 2 * np.pi, az_steps, endpoint=False)
-    T, AZ = np.meshgrid(theta, az, indexing="ij")
-    T = T.ravel()
-    AZ = AZ.ravel()
-    # range to ground plane z = -1.8 m, capped at 80 m
-    with np.errstate(divide="ignore"):
-        rng_ground = np.where(np.sin(T) < -1e-3, -1.8 / np.sin(T), 80.0)
-    r = np.minimum(rng_ground, 80.0)
-    # four box obstacles (azimuth sector, distance)
-    for a0, a1, d in ((0.3, 0.6, 12.0), (1.8, 2.3, 20.0), (3.5, 3.7, 7.0), (5.0, 5.6, 30.0)):
-        hit = (AZ > a0) & (AZ < a1) & (r * np.cos(T) > d)
-        r = np.where(hit, d / np.maximum(np.cos(T), 1e-3), r)
-    r = r + rng.normal(0, 0.01, size=r.shape)
-    x = r * np.cos(T) * np.cos(AZ)
-    y = r * np.cos(T) * np.sin(AZ)
-    z = r * np.sin(T)
-    p = np.stack([x, y, z], axis=1) * 1000.0  # mm
-    p -= p.min(axis=0)
-    xyz = np.rint(p * scale).astype(np.int32)
-    xyz = np.unique(xyz, axis=0)
-    xyz = xyz[rng.permutation(xyz.shape[0])][:n]
-    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
-
-
-def cloud_random(n, bits, seed, a=3, dup_frac=0.0, bitdepth=8):
-    """Uniform random voxels (worst case for neighbourhood structure)."""
-    rng = np.random.default_rng(seed)
-    xyz = rng.integers(0, 1 << bits, size=(n, 3), dtype=np.int32)
-    if dup_frac > 0:
-        k = int(n * dup_frac)
-        src = rng.integers(0, n, size=k)
-        dst = rng.integers(0, n, size=k)
-        xyz[dst] = xyz[src]
-    attrs = rng.integers(0, 1 << bitdepth, size=(n, a), dtype=np.int32)
-    return xyz, attrs
+_sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc13_b200"))
+from pcc_attr_b200.synth import (cloud_cube, cloud_lidar, cloud_random, cloud_shell,  # noqa: E402,F401
+                                 np_morton, sort_cloud)
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,61 @@
+"""CPU tests of the drop-in boundary: the library loads without a GPU, exports
+exactly the symbols include/pcc_attr_b200.h declares, and refuses to compute
+(loudly) when no sm_100 device is present -- there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "pcc_attr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pccb200_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    import pcc_attr_b200 as pb
+
+    lib = pb.lib()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(pb.EXPORTS) == names
+    assert lib.pccb200_abi_version() == 1
+
+
+def test_pod_layout_matches_header():
+    import pcc_attr_b200 as pb
+    from pcc_testlib import QpSet, RahtParams
+
+    assert C.sizeof(pb.RahtParams) == 4 * (6 + 19 + 12 + 1) == C.sizeof(RahtParams)
+    assert C.sizeof(pb.QpSet) == 4 * (1 + 64 + 3 + 32 * 14) == C.sizeof(QpSet)
+    assert C.sizeof(pb.Predictor) == 28 == pb.PREDICTOR_DTYPE.itemsize
+
+
+def test_defaults_need_no_device():
+    import pcc_attr_b200 as pb
+
+    p = pb.default_params()
+    assert (p.prediction_enabled, p.prediction_threshold0, p.prediction_threshold1) == (1, 2, 6)
+    assert list(p.pred_weight_parent)[:4] == [9, 3, 3, 3]
+    assert list(p.pred_weight_child) == [2, 2, 5, 2, 5, 5, 2, 2, 2, 2, 2, 2]
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pcc_attr_b200 as pb
+    from pcc_testlib import make_qpset
+
+    q = pb.QpSet.from_buffer_copy(bytes(make_qpset()))
+    with pytest.raises(pb.PccB200Error):
+        pb.raht_forward(pb.default_params(), q, np.arange(4, dtype=np.int64),
+                        np.zeros((4, 3), dtype=np.int32))

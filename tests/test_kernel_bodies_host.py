@@ -1,0 +1,76 @@
+"""CPU tests of the product's kernel bodies (csrc/raht_core.cuh,
+raht_pipeline.cuh, pcc_arith.cuh) compiled for the host by tests/emu and run
+as in-order loops, against the oracle.  This exercises stage planning, node
+construction, coefficient addressing and the dataflow bookkeeping without a
+GPU; the GPU tests (-m gpu) run the same bodies as CUDA kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from pcc_testlib import *  # noqa
+
+
+def _cmp(xyz, attrs, p, qs, qpo=None):
+    mort, a_s, order = sort_cloud(xyz, attrs)
+    q = qpo[order] if qpo is not None else None
+    orec, ocoef = oracle_raht(1, p, qs, mort, a_s, qpoffs=q)
+    erec, ecoef = emu_raht(1, p, qs, mort, a_s, qpoffs=q)
+    assert np.array_equal(ecoef, ocoef)
+    assert np.array_equal(erec, orec)
+    erec2, _ = emu_raht(0, p, qs, mort, a_s * 0, coeffs=ocoef, qpoffs=q)
+    assert np.array_equal(erec2, orec)
+
+
+def test_arith_golden():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "arith_golden.npz"))
+    e = load_emu()
+    assert [e.emu_isqrt(int(x)) for x in g["xs"]] == g["isqrt"].tolist()
+    assert [e.emu_irsqrt(int(x)) for x in g["xs"]] == g["irsqrt"].tolist()
+    assert [e.emu_fixed_mul(int(a), int(b)) for a, b in zip(g["fa"], g["fb"])] == g["fxmul"].tolist()
+    assert [e.emu_quantize(int(q), int(x)) for q, x in zip(g["qps"], g["qx"])] == g["quant"].tolist()
+    assert [e.emu_scale(int(q), int(x)) for q, x in zip(g["qps"], g["qx"])] == g["scale"].tolist()
+    assert [e.emu_morton_addr(*map(int, p)) for p in g["pts"]] == g["morton"].tolist()
+    assert [e.emu_morton3d_add(int(a), int(b)) for a, b in zip(g["ma"], g["mb"])] == g["madd"].tolist()
+    assert [e.emu_div_approx(int(a), int(b), 0) for a, b in zip(g["da"], g["db"])] == g["divapprox"].tolist()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(prediction=0), dict(subnode=0), dict(haar=1),
+                                dict(ext=0), dict(thr0=0, thr1=1)])
+def test_shell(kw):
+    xyz, attrs = cloud_shell(20000, bits=8, seed=3)
+    for qp in (16, 34):
+        _cmp(xyz, attrs, make_params(**kw), make_qpset(qp=qp))
+
+
+def test_dups_lidar_sparse():
+    for a in (1, 3):
+        xyz, attrs = cloud_shell(20000, bits=7, seed=4, a=a, dups=True)
+        for kw in (dict(), dict(haar=1), dict(ext=0)):
+            _cmp(xyz, attrs, make_params(**kw), make_qpset(qp=28))
+    xyz, attrs = cloud_lidar(30000, seed=2)
+    _cmp(xyz, attrs, make_params(search_range=2500), make_qpset(qp=34))
+    _cmp(xyz, attrs, make_params(search_range=5), make_qpset(qp=34))
+    xyz, attrs = cloud_random(20000, 3, seed=12)
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=34))
+    for bits in (4, 21):
+        xyz, attrs = cloud_random(10000, bits, seed=bits, dup_frac=0.2)
+        _cmp(xyz, attrs, make_params(thr0=0, thr1=1), make_qpset(qp=30))
+
+
+def test_qp_structures_and_edges():
+    rng = np.random.default_rng(7)
+    xyz, attrs = cloud_shell(20000, bits=8, seed=5)
+    qpo = rng.integers(-6, 7, size=(xyz.shape[0], 2)).astype(np.int32)
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=30), qpo)
+    _cmp(xyz, attrs, make_params(), make_qpset(layers=[(40, -2), (36, -1), (32, 0), (28, 1)]))
+    ac = [[(l - c, c - l) for c in range(7)] for l in range(4)]
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=30, ac_qps=ac), qpo)
+    for n in (1, 2, 3, 9):
+        xyz, attrs = cloud_random(n, 3, seed=n)
+        _cmp(xyz, attrs, make_params(), make_qpset(qp=20))
+    xyz = np.tile(np.array([[5, 6, 7]], dtype=np.int32), (6, 1))
+    attrs = rng.integers(0, 256, size=(6, 3)).astype(np.int32)
+    _cmp(xyz, attrs, make_params(), make_qpset(qp=20))
+    xyz = np.array([[0, 0, 0], [2**20, 2**20, 2**20], [2**20 + 1, 2**20, 2**20]], dtype=np.int32)
+    _cmp(xyz, attrs[:3], make_params(thr0=0, thr1=0), make_qpset(qp=20))
