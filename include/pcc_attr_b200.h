@@ -170,13 +170,17 @@ int pccb200_attr_raht_encode_slices(const pccb200_raht_params* params,
 
 /* Device-resident variants (inputs and outputs already in HBM) ------------- */
 
-/* The CUDA stream (cudaStream_t) every call of this library is issued on, so
- * that a caller can order its own work or record events against it. */
-void* pccb200_stream(void);
+/* Calls made from different host threads run concurrently, each on its own
+ * CUDA stream ("lane"); the slices of one *_slices call are spread over lanes
+ * as well.  pccb200_time_begin() records a CUDA event that every lane waits
+ * for, pccb200_time_end() one that waits for every lane, and returns the
+ * elapsed device time between the two in milliseconds. */
+int pccb200_time_begin(void);
+int pccb200_time_end(double* ms_out);
 
 /* As pccb200_attr_raht_encode_slices / a decode counterpart, but every array
  * pointer is a DEVICE pointer on the selected device; slice_offsets stays a
- * host array.  Work is issued on pccb200_stream() and complete on return. */
+ * host array.  Complete on return. */
 int pccb200_attr_raht_encode_slices_dev(const pccb200_raht_params* params,
                                         const pccb200_qpset* qpset,
                                         const int32_t* d_point_qp_offsets,
@@ -196,7 +200,7 @@ int pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
                                         const int32_t* d_coeffs_in);
 
 /* Per-phase device timing (CUDA events around every kernel launch on
- * pccb200_stream()).  Phases: 0 Morton keys + radix sort, 1 tree build
+ * the call's stream).  Phases: 0 Morton keys + radix sort, 1 tree build
  * (histogram, compaction, leaf / merge kernels), 2 block transform (the
  * top-down dataflow kernels), 3 duplicate tail + write-back, 4 gather /
  * scatter / clip, 5 lifting passes.  pccb200_profile_read returns the

@@ -19,8 +19,13 @@
 #include "pcc_attr_b200.h"
 #include <stdio.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <atomic>
 #include <vector>
+
+#include "raht_block_warp.cuh"
 
 namespace pccb200 {
 
@@ -174,7 +179,7 @@ k_tile_count(P pred, int64_t n, int* tileCount)
 // exclusive scan of the tile counts by a single CTA (tile counts are few:
 // n / 2048)
 __global__ void __launch_bounds__(1024)
-k_scan_tiles(int* tileCount, int numTiles)
+k_scan_tiles(int* tileCount, int numTiles, int* total)
 {
   __shared__ int sWarp[32];
   __shared__ int sCarry;
@@ -214,6 +219,8 @@ k_scan_tiles(int* tileCount, int numTiles)
       sCarry = carry + warpOff + x;
     __syncthreads();
   }
+  if (total && threadIdx.x == 0)
+    *total = sCarry;
 }
 
 template<class P, class E>
@@ -301,6 +308,7 @@ struct DeviceExec {
   unsigned long long* ticket = nullptr;  // device word for ordered launches
   Profiler* prof = nullptr;
   int curPhase = 0;
+  const std::atomic<int>* activeCalls = nullptr;  // calls in flight (all lanes)
 
   void phase(int p) { curPhase = p; }
 
@@ -334,6 +342,11 @@ struct DeviceExec {
   void zero(void* p, size_t bytes)
   {
     PCC_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
+  }
+
+  void fill(void* p, int byte, size_t bytes)
+  {
+    PCC_CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, stream));
   }
 
   void upload(void* dst, const void* src, size_t bytes)
@@ -387,18 +400,110 @@ struct DeviceExec {
   }
 
   template<class P, class E>
-  void compact(int64_t n, const P& pred, const E& emit)
+  void compact(int64_t n, const P& pred, const E& emit, int* total = nullptr)
   {
-    if (n <= 0)
+    if (n <= 0) {
+      if (total)
+        zero(total, sizeof(int));
       return;
+    }
     int numTiles = int((n + kTile - 1) / kTile);
     int* tiles = alloc<int>(numTiles);
     Scope sc(*this);
     k_tile_count<P><<<numTiles, kTileThreads, 0, stream>>>(pred, n, tiles);
-    k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, numTiles);
+    k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, numTiles, total);
     k_tile_emit<P, E><<<numTiles, kTileThreads, 0, stream>>>(pred, emit, n, tiles);
     g_launchCount += 3;
     PCC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // One top-down stage.  Default: PrepFn (single-child blocks, qp descent) ->
+  // worklist of the transforming blocks -> warp-cooperative dataflow kernel.
+  // PCCB200_BLOCK_KERNEL=thread selects the thread-per-block body (BlockFn)
+  // instead, for A/B comparison.
+  template<class Fn>
+  void block_stage(const Fn& fn, int64_t nBlocks, int* tzNext)
+  {
+    static const bool threadMode = [] {
+      const char* e = getenv("PCCB200_BLOCK_KERNEL");
+      return e && !strcmp(e, "thread");
+    }();
+    const bool root = fn.P.n == 0;
+    if (threadMode) {
+      if (root) {
+        foreach(1, fn);
+      } else {
+        foreach(nBlocks, PrepFn{fn.cfg, fn.S, fn.P, fn.predInLvl, fn.tz});
+        ordered(nBlocks, SkipSinglesFn<Fn>{fn});
+      }
+      if (tzNext)
+        foreach(1, TzCarryFn{fn.tz, nullptr, int(nBlocks), tzNext});
+      return;
+    }
+    WarpBlockArgs a;
+    a.cfg = fn.cfg;
+    a.qt = fn.qt;
+    a.S = fn.S;
+    a.P = fn.P;
+    a.coef = fn.coef;
+    a.coefStride = fn.coefStride;
+    a.coefBase = fn.coefBase;
+    a.qpLayer = fn.qpLayer;
+    a.acLayer = fn.acLayer;
+    a.predInLvl = fn.predInLvl;
+    a.tz = fn.tz;
+    raht_ab(1, 1, a.ab11a, a.ab11b);
+    int* dCount = alloc<int>(1);
+    if (root) {
+      int one = 1;
+      upload(dCount, &one, sizeof(int));
+      a.worklist = nullptr;
+    } else {
+      foreach(nBlocks, PrepFn{fn.cfg, fn.S, fn.P, fn.predInLvl, nullptr});
+      int32_t* list = alloc<int32_t>(size_t(nBlocks));
+      compact(nBlocks, MultiChildPred{fn.P.first}, WorklistEmit{list}, dCount);
+      a.worklist = list;
+    }
+    a.count = dCount;
+    a.geom = nullptr;
+    if (!root && fn.predInLvl) {
+      a.geom = alloc<int32_t>(size_t(nBlocks) * kGeomStride);
+      Scope sc(*this);
+      k_block_geom<<<unsigned((nBlocks * 32 + 255) / 256), 256, 0, stream>>>(a);
+      g_launchCount++;
+    }
+    PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    static int perSM = 0;
+    if (!perSM) {
+      PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &perSM, k_block_warp, kWarpBlockThreads, 0));
+      if (perSM < 1)
+        perSM = 1;
+    }
+    const int64_t perCta = int64_t(kWarpBlockThreads / 32) * kWarpBlockChunk;
+    int64_t blocks = (nBlocks + perCta - 1) / perCta;
+    // calls in flight share the machine: the persistent grid of each takes
+    // its part (sampled at launch time)
+    const int inFlight = activeCalls ? activeCalls->load() : 1;
+    int64_t cap = int64_t(numSMs) * perSM / (inFlight < 1 ? 1 : inFlight);
+    static const int envCap = [] {
+      const char* e = getenv("PCCB200_BLOCK_GRID");
+      return e ? atoi(e) : 0;
+    }();
+    if (envCap > 0)
+      cap = envCap;
+    if (cap < 8)
+      cap = 8;
+    if (blocks > cap)
+      blocks = cap;
+    {
+      Scope sc(*this);
+      k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
+    }
+    g_launchCount++;
+    PCC_CUDA_CHECK(cudaGetLastError());
+    if (tzNext)
+      foreach(1, TzCarryFn{fn.tz, dCount, 0, tzNext});
   }
 };
 

@@ -268,7 +268,7 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
     DeviceExec::Scope sc(ex);
     k_radix_hist<<<numTiles, kSortThreads, 0, st>>>(kin, n, shift, numTiles, hist);
     k_scan_sum<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
-    k_scan_tiles<<<1, 1024, 0, st>>>(tileSums, scanTiles);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tileSums, scanTiles, nullptr);
     k_scan_apply<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
     k_radix_scatter<<<numTiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift,
                                                        numTiles, hist);

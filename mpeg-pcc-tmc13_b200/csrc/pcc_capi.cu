@@ -7,8 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "exec_cuda.cuh"
 #include "lifting.cuh"
@@ -24,15 +28,36 @@ namespace {
 
 thread_local std::string t_lastError;
 
-struct Context {
-  std::mutex mu;
-  int device = 0;
-  bool ready = false;
+// One lane = one CUDA stream with its own workspace arena, ticket word and
+// event pool.  Every API call runs on one lane; calls from different host
+// threads (slices, attributes, frames are independent work units,
+// tmc3/encoder.cpp:545-568,1052) run on different lanes and overlap on the
+// device.  Lanes are created on demand up to kMaxLanes.
+struct Lane {
   cudaStream_t stream = nullptr;
   Arena arena;
   unsigned long long* ticket = nullptr;
-  int numSMs = 0;
   Profiler prof;
+  bool busy = false;
+};
+
+constexpr int kMaxLanes = 32;
+
+struct Context {
+  std::mutex mu;
+  std::condition_variable cv;
+  int device = 0;
+  bool ready = false;
+  int numSMs = 0;
+  std::atomic<int> active{0};
+  std::vector<std::unique_ptr<Lane>> lanes;
+  // profiling totals over all lanes
+  bool profEnabled = false;
+  double profMs[PCCB200_NUM_PHASES] = {};
+  uint64_t profLaunches[PCCB200_NUM_PHASES] = {};
+  // whole-device timing (pccb200_time_begin / _end)
+  cudaStream_t timeStream = nullptr;
+  cudaEvent_t timeBegin = nullptr, timeEnd = nullptr;
 };
 
 Context&
@@ -74,27 +99,34 @@ ensure_ready(Context& c)
   e = cudaSetDevice(c.device);
   if (e != cudaSuccess)
     return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
-  e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess)
-    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
-  e = cudaMalloc(&c.ticket, 256);
-  if (e != cudaSuccess)
-    return fail(PCCB200_ERR_NOMEM, cudaGetErrorString(e));
   c.numSMs = prop.multiProcessorCount;
   c.ready = true;
   return PCCB200_OK;
 }
 
-DeviceExec
-make_exec(Context& c)
+// must hold c.mu; creates the lane's device objects
+int
+make_lane(Context& c, Lane& l)
 {
-  DeviceExec ex;
-  ex.stream = c.stream;
-  ex.arena = &c.arena;
-  ex.numSMs = c.numSMs;
-  ex.ticket = c.ticket;
-  ex.prof = &c.prof;
-  return ex;
+  cudaError_t e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
+  e = cudaMalloc(&l.ticket, 256);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_NOMEM, cudaGetErrorString(e));
+  return PCCB200_OK;
+}
+
+void
+destroy_lanes(Context& c)
+{
+  for (auto& l : c.lanes) {
+    cudaStreamSynchronize(l->stream);
+    l->arena.release();
+    cudaFree(l->ticket);
+    cudaStreamDestroy(l->stream);
+  }
+  c.lanes.clear();
 }
 
 template<class T>
@@ -115,31 +147,120 @@ to_host(DeviceExec& ex, T* host, const T* dev, size_t n)
     PCC_CUDA_CHECK(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ex.stream));
 }
 
-// runs body(ex) with the context locked and CUDA errors mapped to a status
+// runs body(ex) on a free lane, CUDA errors mapped to a status
 template<class Body>
 int
 with_device(Body body)
 {
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
-  int rc = ensure_ready(c);
-  if (rc != PCCB200_OK)
-    return rc;
+  Lane* lane = nullptr;
+  {
+    std::unique_lock<std::mutex> lock(c.mu);
+    int rc = ensure_ready(c);
+    if (rc != PCCB200_OK)
+      return rc;
+    for (;;) {
+      for (auto& l : c.lanes)
+        if (!l->busy) {
+          lane = l.get();
+          break;
+        }
+      if (lane)
+        break;
+      if (int(c.lanes.size()) < kMaxLanes) {
+        cudaSetDevice(c.device);
+        std::unique_ptr<Lane> l(new Lane);
+        rc = make_lane(c, *l);
+        if (rc != PCCB200_OK)
+          return rc;
+        lane = l.get();
+        c.lanes.push_back(std::move(l));
+        break;
+      }
+      c.cv.wait(lock);
+    }
+    lane->busy = true;
+    lane->prof.enabled = c.profEnabled;
+    ++c.active;
+  }
+  int rc;
   try {
     PCC_CUDA_CHECK(cudaSetDevice(c.device));
-    c.arena.reset();
-    DeviceExec ex = make_exec(c);
+    lane->arena.reset();
+    DeviceExec ex;
+    ex.stream = lane->stream;
+    ex.arena = &lane->arena;
+    ex.numSMs = c.numSMs;
+    ex.ticket = lane->ticket;
+    ex.prof = &lane->prof;
+    ex.activeCalls = &c.active;
     rc = body(ex);
-    PCC_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    c.prof.resolve();
+    PCC_CUDA_CHECK(cudaStreamSynchronize(lane->stream));
+    lane->prof.resolve();
     if (rc != PCCB200_OK && t_lastError.empty())
       t_lastError = "invalid argument";
-    return rc;
   } catch (const CudaError& e) {
     cudaGetLastError();
-    return fail(e.code == cudaErrorMemoryAllocation ? PCCB200_ERR_NOMEM : PCCB200_ERR_CUDA,
-                std::string(e.what) + ": " + cudaGetErrorString(e.code));
+    rc = fail(e.code == cudaErrorMemoryAllocation ? PCCB200_ERR_NOMEM : PCCB200_ERR_CUDA,
+              std::string(e.what) + ": " + cudaGetErrorString(e.code));
   }
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
+      c.profMs[i] += lane->prof.ms[i];
+      c.profLaunches[i] += lane->prof.launches[i];
+      lane->prof.ms[i] = 0;
+      lane->prof.launches[i] = 0;
+    }
+    lane->busy = false;
+    c.active--;
+  }
+  c.cv.notify_one();
+  return rc;
+}
+
+// runs fn(i) for i in [0, n) on up to maxThreads host threads; returns the
+// first non-zero status
+template<class Fn>
+int
+parallel_for(int n, int maxThreads, Fn fn)
+{
+  if (n == 1 || maxThreads <= 1) {
+    for (int i = 0; i < n; i++) {
+      int rc = fn(i);
+      if (rc)
+        return rc;
+    }
+    return 0;
+  }
+  std::atomic<int> next{0}, status{0};
+  std::string err;
+  std::mutex errMu;
+  auto worker = [&] {
+    for (;;) {
+      int i = next.fetch_add(1);
+      if (i >= n)
+        return;
+      int rc = fn(i);
+      if (rc) {
+        int expected = 0;
+        if (status.compare_exchange_strong(expected, rc)) {
+          std::lock_guard<std::mutex> g(errMu);
+          err = t_lastError;
+        }
+      }
+    }
+  };
+  int nt = n < maxThreads ? n : maxThreads;
+  std::vector<std::thread> ts;
+  for (int t = 1; t < nt; t++)
+    ts.emplace_back(worker);
+  worker();
+  for (auto& t : ts)
+    t.join();
+  if (status.load())
+    t_lastError = err;
+  return status.load();
 }
 
 int
@@ -168,48 +289,41 @@ raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset
   });
 }
 
-// all array pointers are device pointers; sliceOffsets is a host array
+// one slice: sort, gather, transform, clip + scatter back.  All array
+// pointers are device pointers addressing the slice's first point; coefficient
+// component k sits at dCoef + k * coefStride.
 int
-attr_raht_core(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
-               const pccb200_qpset* qpset, const int32_t* dQpoIn, const int32_t* dXyz,
-               const int32_t* dAttrsIn, int32_t* dAttrsOut, int A, int bitdepth,
-               const int64_t* sliceOffsets, int numSlices, int32_t* dCoef)
+attr_raht_slice(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
+                const pccb200_qpset* qpset, const int32_t* dQpoIn, const int32_t* dXyz,
+                const int32_t* dAttrsIn, int32_t* dAttrsOut, int A, int bitdepth, int n,
+                int32_t* dCoef, int64_t coefStride)
 {
-  const int64_t total = sliceOffsets[numSlices];
-  int64_t* dKeys = ex.alloc<int64_t>(size_t(total));
-  int32_t* dOrder = ex.alloc<int32_t>(size_t(total));
-  int32_t* dAttrs = ex.alloc<int32_t>(size_t(total) * A);
-  int32_t* dQpo = dQpoIn ? ex.alloc<int32_t>(size_t(total) * 2) : nullptr;
+  int64_t* dKeys = ex.alloc<int64_t>(size_t(n));
+  int32_t* dOrder = ex.alloc<int32_t>(size_t(n));
+  int32_t* dAttrs = ex.alloc<int32_t>(size_t(n) * A);
+  int32_t* dQpo = dQpoIn ? ex.alloc<int32_t>(size_t(n) * 2) : nullptr;
   const int32_t clipMax = (1 << bitdepth) - 1;
-  for (int s = 0; s < numSlices; s++) {
-    const int64_t o = sliceOffsets[s];
-    const int n = int(sliceOffsets[s + 1] - o);
-    device_morton_sort(ex, dXyz + 3 * o, n, dKeys + o, dOrder + o);
-    const unsigned g = grid_for(n, ex.numSMs);
-    ex.phase(kPhaseGather);
-    if (forward) {
-      DeviceExec::Scope sc(ex);
-      k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dAttrsIn + o * A, dOrder + o, n, A,
-                                                       dAttrs + o * A);
-      g_launchCount++;
-    }
-    if (dQpoIn) {
-      DeviceExec::Scope sc(ex);
-      k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dQpoIn + 2 * o, dOrder + o, n, 2,
-                                                       dQpo + 2 * o);
-      g_launchCount++;
-    }
-    int rc = raht_run(ex, *params, *qpset, forward, dKeys + o, dAttrs + o * A,
-                      dQpoIn ? dQpo + 2 * o : nullptr, dCoef + o, total, A, n);
-    if (rc != PCCB200_OK)
-      return fail(rc, "invalid parameters");
-    ex.phase(kPhaseGather);
-    {
-      DeviceExec::Scope sc(ex);
-      k_scatter_rows_clip<<<g, 256, 0, ex.stream>>>(dAttrs + o * A, dOrder + o, n, A, clipMax,
-                                                    dAttrsOut + o * A);
-      g_launchCount++;
-    }
+  device_morton_sort(ex, dXyz, n, dKeys, dOrder);
+  const unsigned g = grid_for(n, ex.numSMs);
+  ex.phase(kPhaseGather);
+  if (forward) {
+    DeviceExec::Scope sc(ex);
+    k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dAttrsIn, dOrder, n, A, dAttrs);
+    g_launchCount++;
+  }
+  if (dQpoIn) {
+    DeviceExec::Scope sc(ex);
+    k_gather_rows<int32_t><<<g, 256, 0, ex.stream>>>(dQpoIn, dOrder, n, 2, dQpo);
+    g_launchCount++;
+  }
+  int rc = raht_run(ex, *params, *qpset, forward, dKeys, dAttrs, dQpo, dCoef, coefStride, A, n);
+  if (rc != PCCB200_OK)
+    return fail(rc, "invalid parameters");
+  ex.phase(kPhaseGather);
+  {
+    DeviceExec::Scope sc(ex);
+    k_scatter_rows_clip<<<g, 256, 0, ex.stream>>>(dAttrs, dOrder, n, A, clipMax, dAttrsOut);
+    g_launchCount++;
   }
   PCC_CUDA_CHECK(cudaGetLastError());
   return PCCB200_OK;
@@ -231,6 +345,10 @@ check_slices(const void* params, const void* qpset, const void* xyz, const void*
   return PCCB200_OK;
 }
 
+constexpr int kMaxSliceThreads = 16;
+
+// host pointers: every slice is staged, transformed and returned on its own
+// lane; slices overlap on the device
 int
 attr_raht_common(bool forward, const pccb200_raht_params* params, const pccb200_qpset* qpset,
                  const int32_t* qpo, const int32_t* xyz, int32_t* attrs, int A,
@@ -241,21 +359,30 @@ attr_raht_common(bool forward, const pccb200_raht_params* params, const pccb200_
   if (rc != PCCB200_OK)
     return rc;
   const int64_t total = sliceOffsets[numSlices];
-  return with_device([&](DeviceExec& ex) -> int {
-    int32_t* dXyz = to_device(ex, xyz, size_t(total) * 3);
-    int32_t* dAttrsIn = forward ? to_device(ex, attrs, size_t(total) * A) : nullptr;
-    int32_t* dQpoIn = qpo ? to_device(ex, qpo, size_t(total) * 2) : nullptr;
-    int32_t* dCoef = forward ? ex.alloc<int32_t>(size_t(total) * A)
-                             : to_device(ex, coeffs, size_t(total) * A);
-    int32_t* dOut = ex.alloc<int32_t>(size_t(total) * A);
-    int rc2 = attr_raht_core(ex, forward, params, qpset, dQpoIn, dXyz, dAttrsIn, dOut, A,
-                             bitdepth, sliceOffsets, numSlices, dCoef);
-    if (rc2 != PCCB200_OK)
-      return rc2;
-    to_host(ex, attrs, dOut, size_t(total) * A);
-    if (forward)
-      to_host(ex, coeffs, dCoef, size_t(total) * A);
-    return PCCB200_OK;
+  return parallel_for(numSlices, kMaxSliceThreads, [&](int s) -> int {
+    const int64_t o = sliceOffsets[s];
+    const int n = int(sliceOffsets[s + 1] - o);
+    return with_device([&](DeviceExec& ex) -> int {
+      int32_t* dXyz = to_device(ex, xyz + 3 * o, size_t(n) * 3);
+      int32_t* dAttrsIn = forward ? to_device(ex, attrs + o * A, size_t(n) * A) : nullptr;
+      int32_t* dQpoIn = qpo ? to_device(ex, qpo + 2 * o, size_t(n) * 2) : nullptr;
+      int32_t* dCoef = ex.alloc<int32_t>(size_t(n) * A);
+      if (!forward)
+        for (int k = 0; k < A; k++)
+          PCC_CUDA_CHECK(cudaMemcpyAsync(dCoef + size_t(k) * n, coeffs + k * total + o,
+                                         size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                         ex.stream));
+      int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+      int rc2 = attr_raht_slice(ex, forward, params, qpset, dQpoIn, dXyz, dAttrsIn, dOut, A,
+                                bitdepth, n, dCoef, n);
+      if (rc2 != PCCB200_OK)
+        return rc2;
+      to_host(ex, attrs + o * A, dOut, size_t(n) * A);
+      if (forward)
+        for (int k = 0; k < A; k++)
+          to_host(ex, coeffs + k * total + o, dCoef + size_t(k) * n, size_t(n));
+      return PCCB200_OK;
+    });
   });
 }
 
@@ -268,11 +395,17 @@ attr_raht_common_dev(bool forward, const pccb200_raht_params* params,
   int rc = check_slices(params, qpset, dXyz, dAttrs, dCoef, A, bitdepth, sliceOffsets, numSlices);
   if (rc != PCCB200_OK)
     return rc;
-  return with_device([&](DeviceExec& ex) -> int {
-    // in-place on the caller's attribute buffer: the gather reads it before
-    // the final scatter overwrites it
-    return attr_raht_core(ex, forward, params, qpset, dQpo, dXyz, dAttrs, dAttrs, A, bitdepth,
-                          sliceOffsets, numSlices, dCoef);
+  const int64_t total = sliceOffsets[numSlices];
+  return parallel_for(numSlices, kMaxSliceThreads, [&](int s) -> int {
+    const int64_t o = sliceOffsets[s];
+    const int n = int(sliceOffsets[s + 1] - o);
+    return with_device([&](DeviceExec& ex) -> int {
+      // in place on the caller's attribute buffer: the gather reads the slice
+      // before the final scatter overwrites it
+      return attr_raht_slice(ex, forward, params, qpset, dQpo ? dQpo + 2 * o : nullptr,
+                             dXyz + 3 * o, dAttrs + o * A, dAttrs + o * A, A, bitdepth, n,
+                             dCoef + o, total);
+    });
   });
 }
 
@@ -322,11 +455,16 @@ pccb200_set_device(int device)
   if (device < 0)
     return fail(PCCB200_ERR_INVALID_ARG, "negative device index");
   if (c.ready && device != c.device) {
+    if (c.active.load())
+      return fail(PCCB200_ERR_INVALID_ARG, "calls in flight on the current device");
     cudaSetDevice(c.device);
-    cudaStreamSynchronize(c.stream);
-    c.arena.release();
-    cudaFree(c.ticket);
-    cudaStreamDestroy(c.stream);
+    destroy_lanes(c);
+    if (c.timeStream) {
+      cudaEventDestroy(c.timeBegin);
+      cudaEventDestroy(c.timeEnd);
+      cudaStreamDestroy(c.timeStream);
+      c.timeStream = nullptr;
+    }
     c.ready = false;
   }
   c.device = device;
@@ -439,14 +577,51 @@ pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
                               const_cast<int32_t*>(d_coeffs_in));
 }
 
-void*
-pccb200_stream(void)
+// Device-side timing across all lanes: begin() records an event that every
+// lane's stream waits for; end() records one event that waits for every
+// lane's stream and returns the elapsed milliseconds between the two.
+int
+pccb200_time_begin(void)
 {
   Context& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
-  if (ensure_ready(c) != PCCB200_OK)
-    return nullptr;
-  return c.stream;
+  int rc = ensure_ready(c);
+  if (rc != PCCB200_OK)
+    return rc;
+  cudaSetDevice(c.device);
+  if (!c.timeStream) {
+    cudaStreamCreateWithFlags(&c.timeStream, cudaStreamNonBlocking);
+    cudaEventCreate(&c.timeBegin);
+    cudaEventCreate(&c.timeEnd);
+  }
+  cudaEventRecord(c.timeBegin, c.timeStream);
+  for (auto& l : c.lanes)
+    cudaStreamWaitEvent(l->stream, c.timeBegin, 0);
+  return PCCB200_OK;
+}
+
+int
+pccb200_time_end(double* ms_out)
+{
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!c.timeStream || !ms_out)
+    return fail(PCCB200_ERR_INVALID_ARG, "pccb200_time_begin not called");
+  cudaSetDevice(c.device);
+  for (auto& l : c.lanes) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(e, l->stream);
+    cudaStreamWaitEvent(c.timeStream, e, 0);
+    cudaEventDestroy(e);
+  }
+  cudaEventRecord(c.timeEnd, c.timeStream);
+  cudaEventSynchronize(c.timeEnd);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c.timeBegin, c.timeEnd) != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, "cudaEventElapsedTime failed");
+  *ms_out = ms;
+  return PCCB200_OK;
 }
 
 void
@@ -454,7 +629,7 @@ pccb200_profile_enable(int enable)
 {
   Context& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
-  c.prof.enabled = enable != 0;
+  c.profEnabled = enable != 0;
 }
 
 void
@@ -463,8 +638,8 @@ pccb200_profile_reset(void)
   Context& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
   for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
-    c.prof.ms[i] = 0;
-    c.prof.launches[i] = 0;
+    c.profMs[i] = 0;
+    c.profLaunches[i] = 0;
   }
 }
 
@@ -474,8 +649,8 @@ pccb200_profile_read(double ms_out[PCCB200_NUM_PHASES], uint64_t launches_out[PC
   Context& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
   for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
-    ms_out[i] = c.prof.ms[i];
-    launches_out[i] = c.prof.launches[i];
+    ms_out[i] = c.profMs[i];
+    launches_out[i] = c.profLaunches[i];
   }
 }
 

@@ -325,6 +325,12 @@ lut_log(int64_t aq)
   return kLog[aq < 15 ? int(aq) : 15];
 }
 
+// A reconstruction slot that has not been written yet at the current stage
+// (the stage's rec array is filled with 0x80 bytes before its blocks run).
+// The warp kernel polls the value itself instead of a separate ready flag:
+// one L2 round trip per dependency instead of two.
+constexpr int64_t kRecNotReady = int64_t(0x8080808080808080ull);
+
 // state words of the zero-run look-back
 constexpr int kTzNone = 0;         // nothing published yet
 constexpr int kTzTransparent = 1;  // block adds `value` zeros, resets nothing
@@ -332,6 +338,122 @@ constexpr int kTzExit = 2;         // `value` is the counter after the block
 PCC_HD int tz_pack(int status, int value) { return (value << 2) | status; }
 PCC_HD int tz_status(int w) { return w & 3; }
 PCC_HD int tz_value(int w) { return w >> 2; }
+
+
+// tables of findNeighbours / intraDcPred (RAHT.cpp:314-326,375-377,438-440)
+PCC_HD int neigh_mask(int i)
+{
+  const uint8_t k[19] = {255, 240, 204, 170, 192, 160, 136, 3, 5, 15,
+                         17,  51,  85,  10,  34,  12,  68,  48, 80};
+  return k[i];
+}
+PCC_HD int neigh_offset(int i)
+{
+  const uint8_t k[19] = {0, 35, 21, 14, 49, 42, 28, 1,  2, 3,
+                         4, 5,  6,  10, 12, 17, 20, 33, 34};
+  return k[i];
+}
+PCC_HD int occu_shift(int i)
+{
+  const uint8_t k[12] = {6, 5, 4, 3, 2, 1, 3, 1, 2, 1, 2, 3};
+  return k[i];
+}
+
+// index in parent stage P of neighbour i (1..18) of parent p, or -1: the node
+// must exist and lie within searchRange entries of p (findNeighbour,
+// RAHT.cpp:272-293,342-367)
+PCC_HD int
+find_parent_neighbour(const Stage& P, int p, int plevel, int64_t cur, int64_t base, int i,
+                      int searchRange)
+{
+  const int64_t np = int64_t(morton3d_add(uint64_t(base), uint64_t(neigh_offset(i))));
+  int lo, hi;
+  if (np >= cur) {
+    lo = p;
+    hi = (int64_t(p) + searchRange + 1 < P.n) ? p + searchRange + 1 : P.n;
+  } else {
+    lo = (p > searchRange) ? p - searchRange : 0;
+    hi = p;
+  }
+  const int end = hi;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((P.key[mid] >> plevel) < np)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return (lo < end && (P.key[lo] >> plevel) == np) ? lo : -1;
+}
+
+// Region qps carried down by the children of one block.  expandLevel
+// (RAHT.cpp:210-264) restores weights and sums but never undoes
+// reduceLevel's pairwise qp average (RAHT.cpp:187-188): the first child of a
+// block inherits the parent's descent value and the first node of each
+// right-hand subtree of the block's binary merge tree carries that subtree's
+// average.  parentDown == nullptr for the root block (total average).
+PCC_HD void
+descend_qps(const Stage& S, int c0, int c1, const int32_t* parentDown)
+{
+  int32_t up[8][2], down[8][2];
+  int firstOf[8], child[8];
+  uint32_t has = 0;
+  for (int j = 0; j < 8; j++) {
+    firstOf[j] = j;
+    child[j] = -1;
+    up[j][0] = up[j][1] = 0;
+    down[j][0] = down[j][1] = 0;
+  }
+  for (int c = c0; c < c1; c++) {
+    int slot = int((S.key[c] >> S.level) & 7);
+    child[slot] = c;
+    has |= 1u << slot;
+    up[slot][0] = S.qpUp[2 * c];
+    up[slot][1] = S.qpUp[2 * c + 1];
+  }
+  for (int step = 1; step < 8; step <<= 1)
+    for (int lo = 0; lo < 8; lo += 2 * step) {
+      int hi = lo + step;
+      if (!((has >> hi) & 1))
+        continue;
+      has &= ~(1u << hi);
+      if (!((has >> lo) & 1)) {
+        has |= 1u << lo;
+        firstOf[lo] = firstOf[hi];
+        up[lo][0] = up[hi][0];
+        up[lo][1] = up[hi][1];
+        continue;
+      }
+      down[firstOf[hi]][0] = up[hi][0];
+      down[firstOf[hi]][1] = up[hi][1];
+      up[lo][0] = (up[lo][0] + up[hi][0]) >> 1;
+      up[lo][1] = (up[lo][1] + up[hi][1]) >> 1;
+    }
+  down[firstOf[0]][0] = parentDown ? parentDown[0] : up[0][0];
+  down[firstOf[0]][1] = parentDown ? parentDown[1] : up[0][1];
+  for (int j = 0; j < 8; j++)
+    if (child[j] >= 0) {
+      S.qpDown[2 * child[j]] = down[j][0];
+      S.qpDown[2 * child[j] + 1] = down[j][1];
+    }
+}
+
+// zero-run counter after block q-1, i.e. the resolved value of word q
+// (decoupled look-back: walk back over transparent blocks to the nearest
+// published exit state)
+PCC_HD int
+tz_lookback(const int* tz, int q)
+{
+  int acc = 0;
+  for (;; q--) {
+    int w;
+    while (tz_status(w = ld_acquire(&tz[q])) == kTzNone)
+      spin_pause();
+    if (tz_status(w) == kTzExit)
+      return tz_value(w) + acc;
+    acc += tz_value(w);
+  }
+}
 
 struct BlockFn {
   RahtConfig cfg;
@@ -358,19 +480,7 @@ struct BlockFn {
       spin_pause();
   }
 
-  // zero-run counter on entry to block p (decoupled look-back)
-  PCC_HD int lookback(int p) const
-  {
-    int acc = 0;
-    for (int q = p;; q--) {  // word q is the state after block q-1
-      int w;
-      while (tz_status(w = ld_acquire(&tz[q])) == kTzNone)
-        spin_pause();
-      if (tz_status(w) == kTzExit)
-        return tz_value(w) + acc;
-      acc += tz_value(w);
-    }
-  }
+  PCC_HD int lookback(int p) const { return tz_lookback(tz, p); }
 
   PCC_HD void operator()(int64_t pb) const
   {
@@ -405,51 +515,14 @@ struct BlockFn {
     }
     const int nodeCnt = cfg.ext ? c1 - c0 : 0;
 
-    //-- region qps carried down (see DESIGN.md "qp descent"): expandLevel
-    //   (RAHT.cpp:210-264) never undoes reduceLevel's pairwise average, so the
-    //   first child of a block inherits the parent's value and the first node
-    //   of each right-hand subtree carries that subtree's average.
+    //-- region qps carried down (written by PrepFn for non-root stages)
     if (cfg.hasQp) {
-      int32_t up[8][2];
-      int firstOf[8];
-      uint32_t has = occ;
-      for (int j = 0; j < 8; j++) {
-        firstOf[j] = j;
-        up[j][0] = up[j][1] = 0;
-        if (child[j] >= 0) {
-          up[j][0] = S.qpUp[2 * child[j]];
-          up[j][1] = S.qpUp[2 * child[j] + 1];
-        }
-      }
-      int32_t down[8][2];
-      for (int step = 1; step < 8; step <<= 1)
-        for (int lo = 0; lo < 8; lo += 2 * step) {
-          int hi = lo + step;
-          if (!((has >> hi) & 1))
-            continue;
-          has &= ~(1u << hi);
-          if (!((has >> lo) & 1)) {
-            has |= 1u << lo;
-            firstOf[lo] = firstOf[hi];
-            up[lo][0] = up[hi][0];
-            up[lo][1] = up[hi][1];
-            continue;
-          }
-          down[firstOf[hi]][0] = up[hi][0];
-          down[firstOf[hi]][1] = up[hi][1];
-          up[lo][0] = (up[lo][0] + up[hi][0]) >> 1;
-          up[lo][1] = (up[lo][1] + up[hi][1]) >> 1;
-        }
-      // slot 0 now holds the whole block: its first child takes the parent's
-      // descent value (the root block: the total average)
-      down[firstOf[0]][0] = root ? up[0][0] : P.qpDown[2 * p];
-      down[firstOf[0]][1] = root ? up[0][1] : P.qpDown[2 * p + 1];
+      if (root)
+        descend_qps(S, c0, c1, nullptr);
       for (int j = 0; j < 8; j++)
         if (child[j] >= 0) {
-          S.qpDown[2 * child[j]] = down[j][0];
-          S.qpDown[2 * child[j] + 1] = down[j][1];
-          nodeQp[j][0] = down[j][0] >> 4;
-          nodeQp[j][1] = down[j][1] >> 4;
+          nodeQp[j][0] = S.qpDown[2 * child[j]] >> 4;
+          nodeQp[j][1] = S.qpDown[2 * child[j] + 1] >> 4;
         }
     }
 
@@ -475,39 +548,14 @@ struct BlockFn {
         const int plevel = S.level + 3;
         const int64_t cur = P.key[p] >> plevel;
         const int64_t base = int64_t(morton3d_add(uint64_t(cur), ~uint64_t(0)));
-        const uint8_t kMasks[19] = {255, 240, 204, 170, 192, 160, 136, 3, 5, 15,
-                                    17,  51,  85,  10,  34,  12,  68,  48, 80};
-        const uint8_t kOffs[19] = {0, 35, 21, 14, 49, 42, 28, 1,  2, 3,
-                                   4, 5,  6,  10, 12, 17, 20, 33, 34};
         pidx[0] = p;
         count = 1;
         for (int i = 1; i < 19; i++) {
           pidx[i] = -1;
-          if (!(occ & kMasks[i]))
+          if (!(occ & neigh_mask(i)))
             continue;
-          int64_t np = int64_t(morton3d_add(uint64_t(base), kOffs[i]));
-          // bounded binary search: the neighbour, if present, lies within
-          // searchRange entries of p (RAHT.cpp:342-367)
-          int lo, hi;
-          if (np >= cur) {
-            lo = p;
-            hi = (int64_t(p) + cfg.searchRange + 1 < P.n) ? p + cfg.searchRange + 1 : P.n;
-          } else {
-            lo = (p > cfg.searchRange) ? p - cfg.searchRange : 0;
-            hi = p;
-          }
-          int end = hi;
-          while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if ((P.key[mid] >> plevel) < np)
-              lo = mid + 1;
-            else
-              hi = mid;
-          }
-          if (lo < end && (P.key[lo] >> plevel) == np) {
-            pidx[i] = lo;
-            count++;
-          }
+          pidx[i] = find_parent_neighbour(P, p, plevel, cur, base, i, cfg.searchRange);
+          count += pidx[i] >= 0;
         }
         if (count < cfg.thr1)
           enablePred = false;
@@ -840,6 +888,100 @@ struct BlockFn {
         }
       }
     }
+  }
+};
+
+
+//============================================================================
+// Work of a stage that needs no other block of the same stage, one thread
+// per block: the qp descent, and the complete treatment of blocks with a
+// single child.  Such a block has no coefficients (its DC is inherited,
+// RAHT.cpp:1727-1742, and there is no AC), so its reconstruction is the
+// parent's value passed through; with rahtExtension it is also never
+// predicted (RAHT.cpp:1399-1401).  Chains of single-child levels dominate
+// sparse (LiDAR) clouds; taking them out leaves the ordered dataflow kernel
+// with the blocks that really transform.
+
+struct PrepFn {
+  RahtConfig cfg;
+  Stage S;
+  Stage P;
+  int predInLvl;
+  int* tzByBlock;  // block-indexed look-back words (or null): a single-child
+                   // block publishes "transparent, 0 coefficients"
+  PCC_HD void operator()(int64_t pb) const
+  {
+    const int p = int(pb);
+    const int c0 = P.first[p], c1 = P.first[p + 1];
+    if (cfg.hasQp)
+      descend_qps(S, c0, c1, &P.qpDown[2 * p]);
+    if (c1 - c0 != 1)
+      return;
+    const int c = c0;
+    const int A = cfg.A;
+    if (predInLvl) {
+      int count = 0;
+      if (cfg.ext) {
+        count = 19;
+      } else if (P.nn[p] >= cfg.thr0) {
+        const int plevel = S.level + 3;
+        const int64_t cur = P.key[p] >> plevel;
+        const int64_t base = int64_t(morton3d_add(uint64_t(cur), ~uint64_t(0)));
+        const int occ = P.occ[p];
+        count = 1;
+        for (int i = 1; i < 19; i++)
+          if (occ & neigh_mask(i))
+            count += find_parent_neighbour(P, p, plevel, cur, base, i, cfg.searchRange) >= 0;
+      }
+      S.nn[c] = count;
+    }
+    const int wgt = S.weight[c];
+    for (int k = 0; k < A; k++) {
+      int64_t v = P.recUs[size_t(p) * A + k];
+      int64_t x = cfg.ext ? v : v * (int64_t(1) << (kFracBits - 2));
+      S.recUs[size_t(c) * A + k] = cfg.ext ? x : fx_round(x * 4);
+      if (!cfg.haar && wgt > 1)
+        x = scale_rsqrt(x, wgt);
+      S.rec[size_t(c) * A + k] = cfg.ext ? x : fx_round(x);
+    }
+    P.done[p] = 1;
+    if (tzByBlock)
+      tzByBlock[p + 1] = tz_pack(kTzTransparent, 0);
+  }
+};
+
+// blocks that the ordered kernel has to run
+struct MultiChildPred {
+  const int32_t* first;
+  PCC_HD bool operator()(int64_t p) const { return first[p + 1] - first[p] >= 2; }
+};
+struct WorklistEmit {
+  int32_t* list;
+  PCC_HD void operator()(int64_t rank, int64_t p) const { list[rank] = int32_t(p); }
+};
+
+// run fn(p) only for blocks with at least two children (thread-per-block path)
+template<class Fn>
+struct SkipSinglesFn {
+  Fn fn;
+  PCC_HD void operator()(int64_t p) const
+  {
+    if (fn.P.first[p + 1] - fn.P.first[p] >= 2)
+      fn(p);
+  }
+};
+
+// hand the zero-run counter to the next stage: dst[0] = exit state after the
+// last of n blocks (n from device memory when countPtr != null)
+struct TzCarryFn {
+  const int* tzSrc;
+  const int* countPtr;
+  int hostCount;
+  int* tzDst;
+  PCC_HD void operator()(int64_t) const
+  {
+    int n = countPtr ? *countPtr : hostCount;
+    tzDst[0] = tz_pack(kTzExit, tz_lookback(tzSrc, n));
   }
 };
 

@@ -6,17 +6,24 @@
 // Executor concept:
 //   T*   alloc<T>(size_t n)                 workspace memory (uninitialised)
 //   void phase(int p)                        tag following launches (profiling)
-//   void zero(void* p, size_t bytes)
+//   void zero(void* p, size_t bytes);  void fill(void* p, int byte, size_t bytes)
 //   void upload(void* dst, const void* src, size_t bytes)      host -> exec
 //   void download(void* dst, const void* src, size_t bytes)    exec -> host, synchronous
 //   void foreach(int64_t n, F f)            f(i) for i in [0, n), any order
 //   void ordered(int64_t n, F f)            f(i) with block-level dataflow:
 //                                           f may spin on flags set by f(j), j < i
-//   void compact(int64_t n, Pred p, Emit e) e(rank, i) for every i with p(i),
-//                                           rank = number of j < i with p(j)
+//   void compact(int64_t n, Pred p, Emit e, int* total = nullptr)
+//                                           e(rank, i) for every i with p(i),
+//                                           rank = number of j < i with p(j);
+//                                           *total (executor memory) = count
+//   void block_stage(BlockFn fn, int64_t nBlocks, int* tzNext)
+//                                           one top-down stage; see exec_cuda.cuh
 //
 // Mirrors the control flow of uraht_process (tmc3/RAHT.cpp:977-1976).
 #pragma once
+
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -162,6 +169,12 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   std::vector<StagePlan> plan = plan_stages(hist, nLeaves);
   const bool hasStages = !plan.empty();
   const int numDup = N - nLeaves;
+  if (getenv("PCCB200_DEBUG")) {
+    fprintf(stderr, "[pccb200] N=%d leaves=%d stages:", N, nLeaves);
+    for (auto& st : plan)
+      fprintf(stderr, " L%d:%d", st.level, st.n);
+    fprintf(stderr, "\n");
+  }
 
   //-- leaves
   std::vector<Stage> stages;
@@ -192,22 +205,24 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   ex.phase(2);  // block transform
   int qpLayer = 0;
   if (hasStages) {
-    // zero-run look-back words: one per block of every stage, plus the
-    // initial state
-    int64_t totalBlocks = 1;
-    for (size_t i = 0; i + 1 < stages.size(); i++)
-      totalBlocks += stages[i + 1].n;
-    int* tz = nullptr;
+    // zero-run look-back words: a region of (blocks + 1) words per stage;
+    // word 0 of a region is the counter handed over by the previous stage
     const bool rdoq = forward && !cfg.haar;
+    std::vector<int64_t> tzOff(stages.size() + 1, 0);
+    int* tz = nullptr;
     if (rdoq) {
-      tz = ex.template alloc<int>(size_t(totalBlocks) + 1);
-      ex.zero(tz, (size_t(totalBlocks) + 1) * sizeof(int));
+      int64_t total = 0;
+      for (int si = int(stages.size()) - 1; si >= 0; si--) {
+        tzOff[si] = total;
+        total += (si == int(stages.size()) - 1 ? 1 : stages[si + 1].n) + 1;
+      }
+      tz = ex.template alloc<int>(size_t(total) + 1);
+      ex.zero(tz, (size_t(total) + 1) * sizeof(int));
       int init = tz_pack(kTzExit, 0);
-      ex.upload(tz, &init, sizeof(int));
+      ex.upload(tz + tzOff[stages.size() - 1], &init, sizeof(int));
     }
 
     int acLayer = -1;
-    int64_t blockBase = 0;
     for (int si = int(stages.size()) - 1; si >= 0; si--) {
       qpLayer = qpLayer + 1 < qs.num_layers ? qpLayer + 1 : qs.num_layers - 1;
       acLayer++;
@@ -219,31 +234,27 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
       fn.coefStride = coefStride;
       fn.qpLayer = qpLayer;
       fn.acLayer = acLayer;
-      fn.tz = tz ? tz + blockBase : nullptr;
-      if (si == int(stages.size()) - 1) {
+      fn.tz = tz ? tz + tzOff[si] : nullptr;
+      fn.useFlags = 1;
+      const bool isRoot = si == int(stages.size()) - 1;
+      if (isRoot) {
         fn.P = Stage{};
         fn.P.n = 0;
         fn.coefBase = 0;
         fn.predInLvl = 0;
-        fn.useFlags = 0;
-        ex.foreach(1, fn);
-        blockBase += 1;
-        continue;
-      }
-      fn.P = stages[si + 1];
-      fn.coefBase = fn.P.n;
-      fn.predInLvl = cfg.predictionEnabled;
-      // intra-stage ordering is needed for sub-node prediction (spatial
-      // dependencies) and for the encoder's zero-run counter
-      const bool deps = (cfg.predictionEnabled && cfg.subnode) || rdoq;
-      fn.useFlags = deps;
-      if (deps) {
-        ex.zero(fn.P.done, size_t(fn.P.n) * sizeof(int));
-        ex.ordered(fn.P.n, fn);
       } else {
-        ex.foreach(fn.P.n, fn);
+        fn.P = stages[si + 1];
+        fn.coefBase = fn.P.n;
+        fn.predInLvl = cfg.predictionEnabled;
+        ex.zero(fn.P.done, size_t(fn.P.n) * sizeof(int));
       }
-      blockBase += fn.P.n;
+      // every reconstruction slot of the stage starts as "not ready"
+      ex.fill(fn.S.rec, 0x80, size_t(fn.S.n) * A * sizeof(int64_t));
+      // the executor runs the stage (single-child fast path + ordered
+      // dataflow over the transforming blocks) and hands the zero-run
+      // counter to the next stage's region
+      int* tzNext = (tz && si > 0) ? tz + tzOff[si - 1] : nullptr;
+      ex.block_stage(fn, isRoot ? 1 : fn.P.n, tzNext);
     }
   }
 

@@ -59,7 +59,7 @@ EXPORTS = [
     "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
     "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
     "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
-    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_stream",
+    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_time_begin", "pccb200_time_end",
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
 ]
@@ -85,7 +85,6 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.pccb200_last_error.restype = C.c_char_p
         l.pccb200_kernel_launch_count.restype = C.c_uint64
-        l.pccb200_stream.restype = C.c_void_p
         _lib = l
     return _lib
 
@@ -225,12 +224,16 @@ def lift(forward, preds, qw, num_points_in_lod, attrs):
 
 # ---- device-resident entry points (pointers are raw device addresses) ------
 
-def stream_handle():
-    """cudaStream_t of the library, as an int (for torch.cuda.ExternalStream)."""
-    h = lib().pccb200_stream()
-    if not h:
-        raise PccB200Error(lib().pccb200_last_error().decode())
-    return int(h)
+def time_begin():
+    """Start of a device-timed region spanning every lane (CUDA events)."""
+    _check(lib().pccb200_time_begin())
+
+
+def time_end():
+    """-> elapsed device milliseconds since time_begin()."""
+    ms = C.c_double(0)
+    _check(lib().pccb200_time_end(C.byref(ms)))
+    return float(ms.value)
 
 
 def attr_raht_encode_dev(params, qpset, d_xyz, d_attrs_inout, d_coeffs, n, a, bitdepth=8,

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <vector>
 
+#include "raht_core.cuh"
+
 struct HostExec {
   std::vector<void*> blocks;
   ~HostExec()
@@ -28,6 +30,7 @@ struct HostExec {
   }
   void phase(int) {}
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  void fill(void* p, int byte, size_t bytes) { memset(p, byte, bytes); }
   void upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
   void download(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
   template<class F>
@@ -43,11 +46,27 @@ struct HostExec {
       f(i);
   }
   template<class P, class E>
-  void compact(int64_t n, const P& pred, const E& emit)
+  void compact(int64_t n, const P& pred, const E& emit, int* total = nullptr)
   {
     int64_t rank = 0;
     for (int64_t i = 0; i < n; i++)
       if (pred(i))
         emit(rank++, i);
+    if (total)
+      *total = int(rank);
+  }
+  // one top-down stage, in Morton order: single-child fast path (PrepFn), the
+  // thread-per-block body for the rest, then the zero-run hand-over
+  template<class Fn>
+  void block_stage(const Fn& fn, int64_t nBlocks, int* tzNext)
+  {
+    if (fn.P.n == 0) {
+      fn(0);
+    } else {
+      foreach(nBlocks, pccb200::PrepFn{fn.cfg, fn.S, fn.P, fn.predInLvl, fn.tz});
+      ordered(nBlocks, pccb200::SkipSinglesFn<Fn>{fn});
+    }
+    if (tzNext)
+      pccb200::TzCarryFn{fn.tz, nullptr, int(nBlocks), tzNext}(0);
   }
 };
