@@ -30,7 +30,12 @@ import sys
 import threading
 import time
 
-import numpy as np
+# one hardware work queue per lane: with the default of 8, more than 8 streams
+# alias and a long dataflow kernel of one call blocks the short kernels of
+# another (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc13_b200"))

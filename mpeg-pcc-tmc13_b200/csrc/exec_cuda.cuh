@@ -485,7 +485,12 @@ struct DeviceExec {
     // calls in flight share the machine: the persistent grid of each takes
     // its part (sampled at launch time)
     const int inFlight = activeCalls ? activeCalls->load() : 1;
-    int64_t cap = int64_t(numSMs) * perSM / (inFlight < 1 ? 1 : inFlight);
+    // With several calls in flight the persistent (spinning) CTAs must never
+    // occupy every register file, or the short kernels of the other calls
+    // (sort, tree build, PrepFn ...) queue behind them: leave half the machine.
+    int64_t cap = int64_t(numSMs) * perSM;
+    if (inFlight > 1)
+      cap /= 2 * inFlight;
     static const int envCap = [] {
       const char* e = getenv("PCCB200_BLOCK_GRID");
       return e ? atoi(e) : 0;

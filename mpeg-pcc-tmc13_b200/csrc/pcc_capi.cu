@@ -6,6 +6,8 @@
 // every compute entry point returns PCCB200_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <memory>
@@ -80,6 +82,9 @@ ensure_ready(Context& c)
 {
   if (c.ready)
     return PCCB200_OK;
+  // one hardware queue per lane (effective only if this process has not
+  // created its CUDA context yet; bench.py sets it itself before torch does)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0) {

@@ -273,3 +273,83 @@ def emu_raht(forward, params, qpset, morton, attrs, coeffs=None, qpoffs=None):
                         attrs, coeffs, qpoffs)
     assert r == 0, r
     return a, c
+
+
+# --------------------------------------------------------------------------
+# lifting helpers
+
+PREDICTOR_DTYPE = np.dtype([("neighbor_count", "<u4"), ("predictor_index", "<u4", 3),
+                            ("weight", "<u4", 3)])
+
+
+def synth_predictors(n, lod_count, seed, k=3):
+    """Synthetic LoD structure: cumulative LoD sizes (coarse -> fine, roughly
+    x4 per level) and predictors whose neighbours lie in strictly coarser
+    LoDs with 8-bit weights summing to 256, like AttributeLods::generate
+    produces for the lifting transform."""
+    rng = np.random.default_rng(seed)
+    sizes = np.maximum(1, (n * (0.25 ** np.arange(lod_count - 1, -1, -1))).astype(np.int64))
+    sizes[-1] = max(1, n - int(sizes[:-1].sum()))
+    npl = np.cumsum(sizes).astype(np.uint32)
+    npl[-1] = n
+    preds = np.zeros(n, dtype=PREDICTOR_DTYPE)
+    start = int(npl[0])
+    for l in range(1, lod_count):
+        s, e = int(npl[l - 1]), int(npl[l])
+        m = e - s
+        if m <= 0:
+            continue
+        cnt = rng.integers(1, k + 1, size=m)
+        cnt = np.minimum(cnt, s)
+        idx = rng.integers(0, s, size=(m, 3))
+        w = rng.integers(1, 200, size=(m, 3)).astype(np.int64)
+        for c in (1, 2, 3):
+            sel = cnt == c
+            ww = w[sel, :c]
+            ww = np.maximum(1, (ww * 256) // ww.sum(axis=1, keepdims=True))
+            ww[:, 0] += 256 - ww.sum(axis=1)
+            w[sel, :c] = ww
+            w[sel, c:] = 0
+            idx[sel, c:] = 0
+        preds["neighbor_count"][s:e] = cnt
+        preds["predictor_index"][s:e] = idx
+        preds["weight"][s:e] = w
+    return preds, npl
+
+
+def _pp(preds):
+    return C.cast(preds.ctypes.data, C.POINTER(Predictor))
+
+
+def oracle_quant_weights(preds):
+    lib = load_oracle()
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    lib.oracle_quant_weights(_pp(preds), C.c_int(preds.shape[0]), _ptr(qw, C.c_uint64))
+    return qw
+
+
+def oracle_lift(forward, preds, qw, npl, attrs):
+    lib = load_oracle()
+    a = np.ascontiguousarray(attrs, dtype=np.int64).copy()
+    if a.ndim == 1:
+        a = a[:, None]
+    lib.oracle_lift(C.c_int(1 if forward else 0), _pp(preds), _ptr(qw, C.c_uint64),
+                    C.c_int(a.shape[0]), _ptr(npl, C.c_uint32), C.c_int(len(npl)),
+                    _ptr(a, C.c_int64), C.c_int(a.shape[1]))
+    return a
+
+
+def ref_quant_weights(preds):
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    load_ref().tmc13ref_quant_weights(_pp(preds), C.c_int(preds.shape[0]), _ptr(qw, C.c_uint64))
+    return qw
+
+
+def ref_lift(forward, preds, qw, npl, attrs):
+    a = np.ascontiguousarray(attrs, dtype=np.int64).copy()
+    if a.ndim == 1:
+        a = a[:, None]
+    load_ref().tmc13ref_lift(C.c_int(1 if forward else 0), _pp(preds), _ptr(qw, C.c_uint64),
+                             C.c_int(a.shape[0]), _ptr(npl, C.c_uint32), C.c_int(len(npl)),
+                             _ptr(a, C.c_int64), C.c_int(a.shape[1]))
+    return a

@@ -167,3 +167,37 @@ def test_full_size_properties(b200):
     assert np.array_equal(dec, rec)
     assert coef.shape == (3, xyz.shape[0])
     assert np.abs(rec - attrs).mean() < 16  # lossy but sane at qp 34
+
+
+@pytest.mark.parametrize("a", [1, 3])
+def test_lifting_vs_oracle(b200, a):
+    """quantisation weights and forward / inverse lifting (64-bit atomics per
+    LoD) against the sequential oracle, bit-exact; inverse(forward(x)) is
+    checked against the oracle's inverse as well."""
+    rng = np.random.default_rng(23)
+    for n, lods in ((5000, 6), (300000, 12), (37, 3), (1000000, 3)):
+        preds, npl = synth_predictors(n, lods, seed=n + a)
+        qw_o = oracle_quant_weights(preds)
+        qw_g = b200.quant_weights(preds, npl)
+        assert np.array_equal(qw_g, qw_o)
+        attrs = (rng.integers(0, 256, size=(n, a)).astype(np.int64)) << 8
+        fo = oracle_lift(1, preds, qw_o, npl, attrs)
+        fg = b200.lift(True, preds, qw_g, npl, attrs)
+        assert np.array_equal(fg, fo)
+        io = oracle_lift(0, preds, qw_o, npl, fo)
+        ig = b200.lift(False, preds, qw_g, npl, fg)
+        assert np.array_equal(ig, io)
+
+
+def test_concurrent_calls(b200):
+    """calls from several host threads run on separate lanes and stay exact"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    xyz, attrs = cloud_shell(80000, bits=9, seed=31)
+    params, qpset = make_params(), make_qpset(qp=34)
+    p, q = _as(b200, params, qpset)
+    ref_rec, ref_coef = b200.attr_raht_encode(p, q, xyz, attrs)
+    with ThreadPoolExecutor(max_workers=12) as pool:
+        outs = list(pool.map(lambda _: b200.attr_raht_encode(p, q, xyz, attrs), range(24)))
+    for rec, coef in outs:
+        assert np.array_equal(rec, ref_rec) and np.array_equal(coef, ref_coef)

@@ -132,3 +132,23 @@ def test_live_scalar_helpers():
     # kDivApproxDivisor[i] + 1 == 65536 // (i + 1) for every index the LUT serves
     for b in range(1, 257):
         assert o.oracle_div_approx(1 << 20, b, 0) == r.tmc13ref_div_approx(1 << 20, b, 0)
+
+
+@needs_ref
+@pytest.mark.parametrize("a", [1, 3])
+def test_live_lifting(a):
+    """lift_oracle.c against PCCComputeQuantizationWeights / PCCLiftPredict /
+    PCCLiftUpdate of the compiled reference, on synthetic LoD structures."""
+    rng = np.random.default_rng(17)
+    for n, lods in ((5000, 6), (60000, 10), (37, 3)):
+        preds, npl = synth_predictors(n, lods, seed=n)
+        qw_r = ref_quant_weights(preds)
+        qw_o = oracle_quant_weights(preds)
+        assert np.array_equal(qw_r, qw_o)
+        attrs = (rng.integers(0, 256, size=(n, a)).astype(np.int64)) << 8
+        fr = ref_lift(1, preds, qw_r, npl, attrs)
+        fo = oracle_lift(1, preds, qw_o, npl, attrs)
+        assert np.array_equal(fr, fo)
+        ir = ref_lift(0, preds, qw_r, npl, fr)
+        io = oracle_lift(0, preds, qw_o, npl, fo)
+        assert np.array_equal(ir, io)
