@@ -12,6 +12,7 @@ from golden.make_golden import VARIANTS  # noqa
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -201,3 +202,65 @@ def test_concurrent_calls(b200):
         outs = list(pool.map(lambda _: b200.attr_raht_encode(p, q, xyz, attrs), range(24)))
     for rec, coef in outs:
         assert np.array_equal(rec, ref_rec) and np.array_equal(coef, ref_coef)
+
+
+def test_dropin_translation_unit(b200):
+    """The reference's own C++ entry points (RAHT.h:47-69), defined by the
+    product's drop-in translation unit instead of tmc3/RAHT.cpp and called
+    through the reference-side shim: same results as the oracle."""
+    import ctypes as C
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libtmc13_dropin.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libtmc13_dropin.so not built (make -C oracle dropin)")
+    lib = C.CDLL(path)
+    lib.tmc13ref_raht.restype = C.c_double
+    import pcc_testlib as tl
+
+    rng = np.random.default_rng(5)
+    xyz, attrs = cloud_shell(60000, bits=9, seed=77)
+    qpo = rng.integers(-3, 4, size=(xyz.shape[0], 2)).astype(np.int32)
+    for kw, q in ((dict(), None), (dict(haar=1), None), (dict(ext=0), None), (dict(), qpo)):
+        params, qpset = make_params(**kw), make_qpset(qp=30)
+        mort, a_s, order = sort_cloud(xyz, attrs)
+        qq = q[order] if q is not None else None
+        orec, ocoef = oracle_raht(1, params, qpset, mort, a_s, qpoffs=qq)
+        drec, dcoef, _ = tl._run_raht(lib.tmc13ref_raht, 1, params, qpset, mort, a_s, None, qq)
+        assert np.array_equal(dcoef, ocoef) and np.array_equal(drec, orec)
+        drec2, _, _ = tl._run_raht(lib.tmc13ref_raht, 0, params, qpset, mort, a_s * 0, ocoef, qq)
+        assert np.array_equal(drec2, orec)
+
+
+def test_whole_codec_bitstream(b200, tmp_path):
+    """The reference's tmc3 executable with RAHT.cpp replaced by the drop-in
+    translation unit produces the same bitstream and reconstruction as the
+    unmodified executable, and decodes the reference's bitstream identically
+    (the verification recipe of scripts/Makefile.tmc13-step: md5 of bitstream,
+    encoder reconstruction and decoder output)."""
+    import hashlib
+
+    import codec_harness as ch
+
+    if not (os.path.exists(ch.REF_BIN) and os.path.exists(ch.B200_BIN)):
+        pytest.skip("oracle/_ref/tmc3_{ref,b200} not built (make -C oracle codec)")
+    xyz, rgb = cloud_shell(120000, bits=10, seed=9)
+    ply = str(tmp_path / "in.ply")
+    ch.write_ply(ply, xyz, rgb)
+
+    def md5(p):
+        return hashlib.md5(open(p, "rb").read()).hexdigest()
+
+    for qp in (34, 22):
+        out = {}
+        for name, binary in (("ref", ch.REF_BIN), ("b200", ch.B200_BIN)):
+            b, r = str(tmp_path / f"{name}{qp}.bin"), str(tmp_path / f"{name}{qp}_rec.ply")
+            rc, log = ch.encode(binary, ply, b, r, qp=qp)
+            assert rc == 0, log[-2000:]
+            out[name] = (b, r)
+        assert md5(out["ref"][0]) == md5(out["b200"][0]), "bitstreams differ"
+        assert md5(out["ref"][1]) == md5(out["b200"][1]), "encoder reconstructions differ"
+        d_ref, d_b200 = str(tmp_path / f"dref{qp}.ply"), str(tmp_path / f"db200{qp}.ply")
+        assert ch.decode(ch.REF_BIN, out["ref"][0], d_ref)[0] == 0
+        rc, log = ch.decode(ch.B200_BIN, out["ref"][0], d_b200)
+        assert rc == 0, log[-2000:]
+        assert md5(d_ref) == md5(d_b200) == md5(out["ref"][1])
