@@ -10,7 +10,7 @@ lossy-attrs CTC settings (qp 34, chroma offset -2, prediction + sub-node
 prediction on, search range 2500).  One step = the attribute coder's RAHT hot
 path over one frame: for colour (A=3) and for reflectance (A=1), Morton key +
 sort, gather, forward transform (RDOQ + quantisation + reconstruction), clip
-and write back.  A step processes --frames (default 8) independent frames of
+and write back.  A step processes --frames (default 16) independent frames of
 that shape per GPU, all attribute calls in flight at once (intra-coded frames,
 slices and attributes are independent work units in the reference,
 tmc3/encoder.cpp:545-568,1052); frames shard across GPUs (weak scaling, no
@@ -56,7 +56,7 @@ def workload_config():
         "attributes": "RGB (A=3) + reflectance (A=1), 8-bit",
         "qp": QP,
         "raht": "prediction + sub-node prediction, rahtExtension, RDOQ, search range 2500",
-        "frames_per_step_per_gpu": 8,
+        "frames_per_step_per_gpu": 16,
         "parallelism": "frames shard across GPUs, no data-path collective",
         "l2": "512 MiB written between steps (excluded from timing) to flush L2",
     }
@@ -248,6 +248,34 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
+# sharding helpers (also exercised on CPU with the gloo backend, tests/test_multiprocess.py)
+
+def frame_seeds(rank, frames):
+    """Distinct synthetic frames per rank: the path shards over frames with no
+    exchange."""
+    return [2 + rank * 100 + f for f in range(frames)]
+
+
+def broadcast_pods(blob, dist, device):
+    """Rank 0 owns the flattened parameter PODs; everyone else receives the
+    bytes (the only collective of the path)."""
+    import torch
+
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def reduce_timing(values, dist, device):
+    """max over ranks of per-rank elapsed times"""
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+# ---------------------------------------------------------------------------
 # our arm
 
 def run_ours(args):
@@ -274,15 +302,14 @@ def run_ours(args):
     # parameter PODs: rank 0 owns them, NCCL broadcasts the bytes
     params, qpset = make_pods(pb)
     if distributed:
-        blob = bytes(params) + bytes(qpset)
-        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().numpy().tobytes())
+        if rank != 0:  # only rank 0's values count
+            params, qpset = pb.RahtParams(), pb.QpSet()
+        raw = broadcast_pods(bytes(params) + bytes(qpset), dist, dev)
         params = pb.RahtParams.from_buffer_copy(raw[:C.sizeof(pb.RahtParams)])
         qpset = pb.QpSet.from_buffer_copy(raw[C.sizeof(pb.RahtParams):])
 
     F = args.frames
-    frames = [make_frame(2 + rank * 100 + f) for f in range(F)]
+    frames = [make_frame(sd) for sd in frame_seeds(rank, F)]
     n = frames[0][0].shape[0]
     pool = ThreadPoolExecutor(max_workers=2 * F)
 
@@ -403,9 +430,7 @@ def run_ours(args):
     d2h = F * 2 * (rgb.nbytes + refl.nbytes)
 
     if distributed:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s = reduce_timing([total_ms, e2e_s], dist, dev)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
@@ -481,7 +506,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames", type=int, default=8,
+    ap.add_argument("--frames", type=int, default=16,
                     help="independent frames in flight per GPU per step (intra coding: frames "
                          "are independent work units)")
     args = ap.parse_args()
