@@ -34,6 +34,9 @@ import time
 # alias and a long dataflow kernel of one call blocks the short kernels of
 # another (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# keep stdout to the single JSON line (NCCL prints its version banner there)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
