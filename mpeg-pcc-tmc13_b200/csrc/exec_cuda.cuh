@@ -309,6 +309,9 @@ struct DeviceExec {
   Profiler* prof = nullptr;
   int curPhase = 0;
   const std::atomic<int>* activeCalls = nullptr;  // calls in flight (all lanes)
+  // zero-run regions of the stages of the running call (warp block kernel)
+  TzRegion* dRegions = nullptr;
+  int numRegions = 0;
 
   void phase(int p) { curPhase = p; }
 
@@ -429,7 +432,11 @@ struct DeviceExec {
       return e && !strcmp(e, "thread");
     }();
     const bool root = fn.P.n == 0;
-    if (threadMode) {
+    // AC-coefficient qp offsets make the RDOQ decision matter even for
+    // coefficients that quantise to zero; that (rare) case keeps the exact
+    // counter protocol of the thread-per-block body
+    const bool exactCounter = fn.cfg.isEncoder && !fn.cfg.haar && fn.cfg.numAcLayers > 0;
+    if (threadMode || exactCounter) {
       if (root) {
         foreach(1, fn);
       } else {
@@ -453,6 +460,11 @@ struct DeviceExec {
     a.predInLvl = fn.predInLvl;
     a.tz = fn.tz;
     raht_ab(1, 1, a.ab11a, a.ab11b);
+    static const int experiment = [] {
+      const char* e = getenv("PCCB200_EXPERIMENT");
+      return e ? atoi(e) : 0;
+    }();
+    a.experiment = experiment;
     int* dCount = alloc<int>(1);
     if (root) {
       int one = 1;
@@ -465,6 +477,18 @@ struct DeviceExec {
       a.worklist = list;
     }
     a.count = dCount;
+    if (root || !dRegions) {
+      dRegions = alloc<TzRegion>(32);
+      numRegions = 0;
+    }
+    TzRegion hr;
+    hr.words = fn.tz;
+    hr.lists = fn.tz ? alloc<int>((size_t(nBlocks) + 1) * 8) : nullptr;
+    hr.count = dCount;
+    a.stageIdx = numRegions;
+    upload(dRegions + numRegions, &hr, sizeof(TzRegion));
+    numRegions++;
+    a.regions = dRegions;
     a.geom = nullptr;
     if (!root && fn.predInLvl) {
       a.geom = alloc<int32_t>(size_t(nBlocks) * kGeomStride);
@@ -507,8 +531,7 @@ struct DeviceExec {
     }
     g_launchCount++;
     PCC_CUDA_CHECK(cudaGetLastError());
-    if (tzNext)
-      foreach(1, TzCarryFn{fn.tz, dCount, 0, tzNext});
+    (void)tzNext;  // the run-length queries walk across stages themselves
   }
 };
 

@@ -38,7 +38,22 @@ struct WarpBlockArgs {
   int32_t* geom;            // kGeomStride ints per worklist entry (see k_block_geom)
   const int* count;         // number of worklist entries (device memory)
   int64_t ab11a, ab11b;     // RahtKernel(1, 1), the commonest butterfly
+  int experiment;           // timing experiments only (PCCB200_EXPERIMENT), 0 in production
+  const struct TzRegion* regions;  // zero-run words/lists of every stage so far
+  int stageIdx;                    // index of this stage in regions (0 = root)
 };
+
+// Zero-run bookkeeping of one stage, indexed by worklist rank t:
+// words[t + 1] is block t's state word, lists[(t + 1) * 8 + i] its i-th
+// coefficient in scan order (0: never resets the run, a > 0: resets it unless
+// the run before it is at least a long).
+struct TzRegion {
+  int* words;
+  int* lists;
+  const int* count;
+};
+
+constexpr int kTzClassified = 3;  // word status: list published, outcome pending
 
 constexpr int kWarpBlockThreads = 256;
 constexpr int kWarpBlockChunk = 1;  // blocks claimed per ticket (consecutive blocks in one
@@ -121,36 +136,78 @@ poll_rec(const int64_t* p)
   return v;
 }
 
-// Warp-parallel decoupled look-back: the zero-run counter after block q-1
-// (the resolved value of word q).  32 words are examined per step; transparent
-// blocks are summed through, the walk ends at the nearest published exit
-// state and waits only on words that have not been published at all.
+// RDOQ threshold of a coefficient: the smallest zero-run length tz for which
+// the reference's test (RAHT.cpp:1617-1636)
+//     (Dist2 << 26) < lambda * (Rate(tz) + ((Ratecoeff + 128) >> 8))
+// holds.  Rate(tz) is a non-decreasing step function; it changes at
+// tz = 0,1,2,3,5,7,9 and at tz = 10 + 2^(a-1), a >= 1.  INT_MAX: never.
 __device__ __forceinline__ int
-tz_lookback_warp(const int* tz, int q, const int lane)
+rdoq_threshold(int64_t dist2, int64_t lambda, int rateCoeff)
 {
-  int acc = 0;
-  for (;;) {
-    const int idx = q - lane;
-    const int w = idx >= 0 ? ld_acquire(&tz[idx]) : tz_pack(kTzExit, 0);
-    const int st = tz_status(w);
-    const unsigned exitMask = __ballot_sync(0xffffffffu, st == kTzExit);
-    const unsigned noneMask = __ballot_sync(0xffffffffu, st == kTzNone);
-    const int firstExit = exitMask ? __ffs(exitMask) - 1 : 32;
-    const int firstNone = noneMask ? __ffs(noneMask) - 1 : 32;
-    const int stop = firstExit < firstNone ? firstExit : firstNone;
-    // transparent words nearer than the stopping lane
-    acc += __reduce_add_sync(0xffffffffu, (lane < stop && st == kTzTransparent) ? tz_value(w) : 0);
-    if (firstExit < firstNone)
-      return acc + tz_value(__shfl_sync(0xffffffffu, w, firstExit));
-    q -= stop;  // all 32 transparent (stop == 32), or wait at the unpublished word
-    if (firstNone < 32)
-      __nanosleep(40);
+  const int64_t lhs = dist2 << 26;
+  const int rc = (rateCoeff + 128) >> 8;
+  const int kTz[7] = {0, 1, 2, 3, 5, 7, 9};
+#pragma unroll
+  for (int i = 0; i < 7; i++)
+    if (lhs < lambda * (zero_run_rate(kTz[i]) + rc))
+      return kTz[i];
+  for (int a = 1; a <= 30; a++) {
+    const int tz = 10 + (1 << (a - 1));
+    if (lhs < lambda * (zero_run_rate(tz) + rc))
+      return tz;
   }
+  return 0x7fffffff;
 }
 
-// every kTzCheckpoint-th block resolves its exit state even if it is
-// transparent, which bounds the length of every look-back walk
-constexpr int kTzCheckpoint = 32;
+// Is the run of non-resetting coefficients that ends just before block t of
+// stage a.stageIdx at least A long?  Walks back over the published
+// classification of earlier blocks (this stage, then earlier stages); waits
+// only for blocks that have not classified their coefficients yet, never for
+// another block's own answer.  All lanes execute it uniformly.
+__device__ __forceinline__ bool
+tz_run_at_least(const WarpBlockArgs& a, int t, int A)
+{
+  if (A <= 0)
+    return true;
+  int req = A;   // positions 1..req behind the block must not reset the run
+  int acc = 0;   // positions already verified
+  int s = a.stageIdx;
+  const TzRegion* rg = &a.regions[s];
+  int u = t - 1;
+  for (;;) {
+    if (u < 0) {
+      if (--s < 0)
+        return acc >= req;  // start of the call: the counter starts at 0
+      rg = &a.regions[s];
+      u = *rg->count - 1;
+      continue;
+    }
+    int w;
+    while (tz_status(w = ld_acquire(&rg->words[u + 1])) == kTzNone)
+      __nanosleep(40);
+    const int st = tz_status(w), v = tz_value(w);
+    if (st == kTzExit)
+      return v + acc >= req;
+    if (st == kTzClassified) {
+      const int4 l0 = *reinterpret_cast<const int4*>(&rg->lists[size_t(u + 1) * 8]);
+      const int4 l1 = *reinterpret_cast<const int4*>(&rg->lists[size_t(u + 1) * 8 + 4]);
+      const int li[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+      for (int i = 7; i >= 0; i--)
+        if (i < v) {
+          const int pos = acc + (v - i);
+          if (pos > req)
+            return true;
+          if (li[i] > 0 && pos + li[i] > req)
+            req = li[i] >= 0x40000000 ? 0x7fffffff : pos + li[i];
+        }
+    }
+    acc += v;
+    if (acc >= req)
+      return true;
+    u--;
+  }
+}
 
 // processes block p (worklist rank t); called by all 32 lanes
 __device__ __forceinline__ void
@@ -357,91 +414,114 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     aq += shfl_xor_i64(aq, 16);
     rc += __shfl_xor_sync(0xffffffffu, rc, 8);
     rc += __shfl_xor_sync(0xffffffffu, rc, 16);
-    const int kindMine = aq == 0 ? 0 : (aq < 3 ? 1 : 2);
+    // classification of this lane's coefficient: 0 = never resets the run
+    // (all components quantise to zero); kAlwaysRemoved = RDOQ removes it at
+    // any run length (never resets either); INT_MAX = always resets the run
+    // (sum of |q| >= 3, or RDOQ never fires); otherwise the run length from
+    // which RDOQ removes it
+    constexpr int kAlwaysRemoved = -2;
+    int thrMine = 0;
+    if (aq >= 3) {
+      thrMine = 0x7fffffff;
+    } else if (aq > 0) {
+      thrMine = rdoq_threshold(d2, lam, rc);
+      if (thrMine == 0)
+        thrMine = kAlwaysRemoved;
+    }
 
     // the block's coefficients in scan order, replicated in every lane
-    int kind[8], rcs[8];
-    int64_t d2s[8], lams[8];
+    int thr[8];
 #pragma unroll
-    for (int m = 0; m < 8; m++) {
-      kind[m] = 0;
-      rcs[m] = 0;
-      d2s[m] = 0;
-      lams[m] = 0;
+    for (int m = 0; m < 8; m++)
+      thr[m] = 0;
+    {
+      int n = 0;
+      const int kScan[8] = {0, 4, 2, 1, 6, 5, 3, 7};
+#pragma unroll
+      for (int si = 0; si < 8; si++) {
+        const int idx = kScan[si];
+        const int th = __shfl_sync(0xffffffffu, thrMine, idx);
+        const bool ex = (existsMask >> idx) & 1;  // uniform across the warp
+#pragma unroll
+        for (int m = 0; m < 8; m++)
+          if (ex && m == n)
+            thr[m] = th;
+        n += ex;
+      }
     }
-    int n = 0;
-    const int kScan[8] = {0, 4, 2, 1, 6, 5, 3, 7};
-#pragma unroll
-    for (int si = 0; si < 8; si++) {
-      const int idx = kScan[si];
-      const int kd = __shfl_sync(0xffffffffu, kindMine, idx);
-      const int r = __shfl_sync(0xffffffffu, rc, idx);
-      const int64_t dd = shfl_i64(d2, idx);
-      const int64_t ll = shfl_i64(lam, idx);
-      const bool ex = (existsMask >> idx) & 1;  // uniform across the warp
-#pragma unroll
-      for (int m = 0; m < 8; m++)
-        if (ex && m == n) {
-          kind[m] = kd;
-          rcs[m] = r;
-          d2s[m] = dd;
-          lams[m] = ll;
-        }
-      n += ex;
-    }
-
-    // zero-run protocol, as in BlockFn (all decisions are warp-uniform)
-    const bool zeroMatters = cfg.numAcLayers > 0;
-    int firstSensitive = -1, firstHard = -1, lastHard = -1;
-    bool anySoft = false;
+    bool hasS = false, hasH = false;
+    int lastH = -1;
 #pragma unroll
     for (int m = 0; m < 8; m++)
       if (m < ncoef) {
-        if ((kind[m] == 1 || (kind[m] == 0 && zeroMatters)) && firstSensitive < 0)
-          firstSensitive = m;
-        anySoft |= kind[m] == 1;
-        if (kind[m] == 2) {
-          if (firstHard < 0)
-            firstHard = m;
-          lastHard = m;
+        if (thr[m] == 0x7fffffff) {
+          hasH = true;
+          lastH = m;
+        } else if (thr[m] > 0) {
+          hasS = true;
         }
       }
-    const bool anyHard = lastHard >= 0;
-    bool published = false;
-    if (!anySoft && !anyHard && lane == 0)
-      st_release(&a.tz[t + 1], tz_pack(kTzTransparent, ncoef));
-    if (anyHard) {
-      int tt = 0;
+
+    // publish what is known without looking at any other block
+    const TzRegion rg = a.regions[a.stageIdx];
+    if (hasH) {
+      int tl = 0;
 #pragma unroll
       for (int m = 0; m < 8; m++)
-        if (m > lastHard && m < ncoef)
-          tt = BlockFn::step_tz(tt, kind[m], d2s[m], lams[m], rcs[m], nullptr);
+        if (m > lastH && m < ncoef)
+          tl = tl >= thr[m] ? tl + 1 : 0;
       if (lane == 0)
-        st_release(&a.tz[t + 1], tz_pack(kTzExit, tt));
-      published = true;
+        st_release(&rg.words[t + 1], tz_pack(kTzExit, tl));
+    } else if (!hasS) {
+      if (lane == 0)
+        st_release(&rg.words[t + 1], tz_pack(kTzTransparent, ncoef));
+    } else {
+      int mine = 0;
+#pragma unroll
+      for (int m = 0; m < 8; m++)
+        if (m == lane)
+          mine = thr[m] > 0 ? thr[m] : 0;
+      if (lane < 8)
+        rg.lists[size_t(t + 1) * 8 + lane] = mine;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0)
+        st_release(&rg.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
-    const bool needEntry =
-      firstSensitive >= 0 && (firstHard < 0 || firstSensitive < firstHard);
-    int tt = needEntry ? tz_lookback_warp(a.tz, t, lane) : 0;
+
+    // resolve this block's own decisions
+    bool linked = true;  // the run still reaches back beyond the block
+    int z = 0;           // its length inside the block while linked
+    int tl = 0;          // run length since the last reset inside the block
 #pragma unroll
     for (int m = 0; m < 8; m++)
       if (m < ncoef) {
-        bool f = false;
-        tt = BlockFn::step_tz(tt, kind[m], d2s[m], lams[m], rcs[m], &f);
+        bool f;
+        if (thr[m] <= 0)
+          f = thr[m] == kAlwaysRemoved;
+        else if (thr[m] == 0x7fffffff)
+          f = false;
+        else if (linked)
+          f = a.experiment == 1 ? false : tz_run_at_least(a, t, thr[m] - z);
+        else
+          f = tl >= thr[m];
+        const bool keeps = thr[m] <= 0 || f;
+        if (linked) {
+          if (keeps)
+            z++;
+          else {
+            linked = false;
+            tl = 0;
+          }
+        } else {
+          tl = keeps ? tl + 1 : 0;
+        }
         if (m == myPos)
           flagMine = f;
       }
-    if (!published && needEntry) {
-      if (lane == 0)
-        st_release(&a.tz[t + 1], tz_pack(kTzExit, tt));
-      published = true;
-    }
-    if (!published && (t % kTzCheckpoint) == kTzCheckpoint - 1) {
-      // transparent checkpoint block: resolve the exit state anyway
-      const int e = tz_lookback_warp(a.tz, t, lane) + ncoef;
-      if (lane == 0)
-        st_release(&a.tz[t + 1], tz_pack(kTzExit, e));
-    }
+    if (hasS && !hasH && lane == 0)
+      st_release(&rg.words[t + 1],
+                 linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
   }
 
   //-- quantise / dequantise (RAHT.cpp:1672-1723)
