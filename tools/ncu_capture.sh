@@ -14,10 +14,10 @@ for _ in range(int(sys.argv[2])):
     pb.attr_raht_encode(p, q, xyz, rgb)
     pb.attr_raht_encode(p, q, xyz, refl)
 PY
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
+timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 2000 --csv \
   --log-file gpurun_out/launches_r01.csv python /tmp/one_call.py 1000000 2 > gpurun_out/ncu_list.log 2>&1
 # full capture: the three largest stage launches of the second RGB call
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_block_warp -s 43 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_block_warp -s 44 -c 3 \
   -o gpurun_out/block_warp_r01 -f python /tmp/one_call.py 1000000 2 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out
