@@ -222,6 +222,36 @@ typedef struct pccb200_predictor {
   uint32_t weight[3];
 } pccb200_predictor;
 
+/* Flattened LoD-relevant fields of pcc::AttributeParameterSet
+ * (tmc3/hls.h:795-857) plus abh.attr_dist2_delta.  Intra coding,
+ * scalable_lifting_enabled_flag == 0, default point order. */
+#define PCCB200_MAX_LODS 32
+typedef struct pccb200_lod_params {
+  int32_t num_detail_levels;         /* num_detail_levels_minus1 + 1 */
+  int32_t lod_decimation_type;       /* 0 distance, 1 periodic, 2 centroid */
+  int32_t lod_sampling_period[PCCB200_MAX_LODS];
+  int32_t dist2;                     /* aps.dist2 + abh.attr_dist2_delta */
+  int32_t num_pred_nearest_neighbours; /* ..._minus1 + 1, 1..3 */
+  int32_t inter_lod_search_range;
+  int32_t intra_lod_search_range;
+  int32_t intra_lod_prediction_skip_layers; /* >= num_detail_levels: none */
+  int32_t prediction_with_distribution;
+  int32_t lod_neigh_bias[3];
+  int32_t pred_weight_blending;      /* predicting transform only */
+} pccb200_lod_params;
+
+/* Level-of-detail build: AttributeLods::generate (tmc3/AttributeCommon.cpp:45-72)
+ * = buildPredictorsFast (tmc3/PCCTMC3Common.h:2300-2469: Morton sort,
+ * subsampling, the atlas / window nearest-neighbour search, updatePredictors)
+ * + PCCPredictor::computeWeights (+ blendWeights).
+ * xyz: N x 3 positions.  preds_out[N] in predictor order (coarse to fine),
+ * indexes_out[N]: predictor order -> point index, num_points_in_lod_out
+ * [PCCB200_MAX_LODS]: cumulative LoD sizes, *lod_count_out their number. */
+int pccb200_lod_build(const pccb200_lod_params* params, const int32_t* xyz,
+                      int32_t n, pccb200_predictor* preds_out,
+                      uint32_t* indexes_out, uint32_t* num_points_in_lod_out,
+                      int32_t* lod_count_out);
+
 /* qw_out[i] for i in [0, n): PCCComputeQuantizationWeights. */
 int pccb200_quant_weights(const pccb200_predictor* preds, int32_t n,
                           const uint32_t* num_points_in_lod, int32_t lod_count,

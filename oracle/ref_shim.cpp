@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "RAHT.h"
+#include "AttributeCommon.h"
 #include "PCCTMC3Common.h"
 #include "PCCMisc.h"
 #include "quantization.h"
@@ -298,6 +299,66 @@ tmc13ref_lift(
     std::copy(v.begin(), v.end(), attrs);
   }
   return secs;
+}
+
+// AttributeLods::generate (tmc3/AttributeCommon.cpp:45-72), parameters set
+// as tmc3/encoder.cpp:777-818 leaves them.  Returns seconds.
+double
+tmc13ref_lod_build(
+  const pccb200_lod_params* lp,
+  const int32_t* xyz,
+  int n,
+  pccb200_predictor* predsOut,
+  uint32_t* indexesOut,
+  uint32_t* numPointsInLodOut,
+  int32_t* lodCountOut)
+{
+  AttributeParameterSet aps{};
+  aps.attr_encoding = lp->pred_weight_blending
+    ? AttributeEncoding::kPredictingTransform
+    : AttributeEncoding::kLiftingTransform;
+  aps.lod_decimation_type = LodDecimationMethod(lp->lod_decimation_type);
+  aps.canonical_point_order_flag = false;
+  aps.max_points_per_sort_log2_plus1 = 0;
+  aps.num_pred_nearest_neighbours_minus1 = lp->num_pred_nearest_neighbours - 1;
+  aps.num_detail_levels_minus1 = lp->num_detail_levels - 1;
+  aps.dist2 = lp->dist2;
+  aps.inter_lod_search_range = lp->inter_lod_search_range;
+  aps.intra_lod_search_range = lp->intra_lod_search_range;
+  aps.intra_lod_prediction_skip_layers = lp->intra_lod_prediction_skip_layers;
+  aps.predictionWithDistributionEnabled = lp->prediction_with_distribution != 0;
+  aps.lodNeighBias = {lp->lod_neigh_bias[0], lp->lod_neigh_bias[1], lp->lod_neigh_bias[2]};
+  aps.pred_weight_blending_enabled_flag = lp->pred_weight_blending != 0;
+  aps.scalable_lifting_enabled_flag = false;
+  aps.lodSamplingPeriod.assign(
+    lp->lod_sampling_period, lp->lod_sampling_period + PCCB200_MAX_LODS);
+  AttributeBrickHeader abh{};
+  abh.attr_dist2_delta = 0;
+  AttributeInterPredParams ip = mkIntra();
+
+  PCCPointSet3 cloud;
+  cloud.resize(n);
+  for (int i = 0; i < n; i++)
+    cloud[i] = point_t{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+
+  AttributeLods lods;
+  auto t0 = std::chrono::steady_clock::now();
+  lods.generate(aps, abh, n - 1, 0, cloud, ip);
+  auto t1 = std::chrono::steady_clock::now();
+
+  for (int i = 0; i < n; i++) {
+    const auto& p = lods.predictors[i];
+    predsOut[i].neighbor_count = p.neighborCount;
+    for (int j = 0; j < 3; j++) {
+      predsOut[i].predictor_index[j] = j < int(p.neighborCount) ? p.neighbors[j].predictorIndex : 0;
+      predsOut[i].weight[j] = j < int(p.neighborCount) ? uint32_t(p.neighbors[j].weight) : 0;
+    }
+    indexesOut[i] = lods.indexes[i];
+  }
+  *lodCountOut = int(lods.numPointsInLod.size());
+  for (size_t i = 0; i < lods.numPointsInLod.size() && i < PCCB200_MAX_LODS; i++)
+    numPointsInLodOut[i] = lods.numPointsInLod[i];
+  return std::chrono::duration<double>(t1 - t0).count();
 }
 
 }  // extern "C"

@@ -28,6 +28,15 @@ VARIANTS = {
 }
 
 
+LOD_GOLDEN_CASES = [
+    dict(levels=8),
+    dict(levels=8, distribution=0),
+    dict(levels=8, decimation=1),
+    dict(levels=8, decimation=2),
+    dict(levels=8, decimation=0, skip_layers=0, intra_range=64, inter_range=64, blending=1),
+]
+
+
 def clouds():
     rng = np.random.default_rng(2024)
     out = {}
@@ -94,6 +103,19 @@ def main():
         os.path.join(HERE, "arith_golden.npz"), xs=xs, isqrt=isq, irsqrt=irs,
         fa=a, fb=b, fxmul=fx, qps=qps, qx=qx, quant=qq, scale=qs, pts=pts,
         morton=mc, ma=ma, mb=mb, madd=madd, da=da, db=db, divapprox=dv)
+    # level-of-detail build (AttributeLods::generate)
+    lod = {}
+    xyz, _ = cloud_shell(4000, bits=7, seed=3)
+    lod["shell/xyz"] = xyz
+    xyz2, _ = cloud_random(3000, 21, seed=5, dup_frac=0.1)
+    lod["sparse/xyz"] = xyz2
+    for cname in ("shell", "sparse"):
+        for i, kw in enumerate(LOD_GOLDEN_CASES):
+            p, idx, npl = ref_lod_build(make_lod_params(**kw), lod[f"{cname}/xyz"])
+            lod[f"{cname}/{i}/preds"] = p
+            lod[f"{cname}/{i}/indexes"] = idx
+            lod[f"{cname}/{i}/npl"] = npl
+    np.savez_compressed(os.path.join(HERE, "lod_golden.npz"), **lod)
     print("golden vectors written")
 
 

@@ -353,3 +353,71 @@ def ref_lift(forward, preds, qw, npl, attrs):
                              C.c_int(a.shape[0]), _ptr(npl, C.c_uint32), C.c_int(len(npl)),
                              _ptr(a, C.c_int64), C.c_int(a.shape[1]))
     return a
+
+
+# --------------------------------------------------------------------------
+# LoD build helpers
+
+MAX_LODS = 32
+
+
+class LodParams(C.Structure):
+    _fields_ = [
+        ("num_detail_levels", C.c_int32),
+        ("lod_decimation_type", C.c_int32),
+        ("lod_sampling_period", C.c_int32 * MAX_LODS),
+        ("dist2", C.c_int32),
+        ("num_pred_nearest_neighbours", C.c_int32),
+        ("inter_lod_search_range", C.c_int32),
+        ("intra_lod_search_range", C.c_int32),
+        ("intra_lod_prediction_skip_layers", C.c_int32),
+        ("prediction_with_distribution", C.c_int32),
+        ("lod_neigh_bias", C.c_int32 * 3),
+        ("pred_weight_blending", C.c_int32),
+    ]
+
+
+def make_lod_params(levels=12, decimation=0, period=4, dist2=0, k=3, inter_range=1100000,
+                    intra_range=0, skip_layers=None, distribution=1, bias=(1, 1, 1), blending=0):
+    p = LodParams()
+    p.num_detail_levels = levels
+    p.lod_decimation_type = decimation
+    for i in range(MAX_LODS):
+        p.lod_sampling_period[i] = period
+    p.dist2 = dist2
+    p.num_pred_nearest_neighbours = k
+    p.inter_lod_search_range = inter_range
+    p.intra_lod_search_range = intra_range
+    # lifting forces "skip all layers" (tmc3/encoder.cpp:777-780)
+    p.intra_lod_prediction_skip_layers = levels + 1 if skip_layers is None else skip_layers
+    p.prediction_with_distribution = distribution
+    for i in range(3):
+        p.lod_neigh_bias[i] = bias[i]
+    p.pred_weight_blending = blending
+    return p
+
+
+def _run_lod(fn, params, xyz):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    n = xyz.shape[0]
+    preds = np.zeros(n, dtype=PREDICTOR_DTYPE)
+    indexes = np.zeros(n, dtype=np.uint32)
+    npl = np.zeros(MAX_LODS, dtype=np.uint32)
+    cnt = C.c_int32(0)
+    r = fn(C.byref(params), _ptr(xyz, C.c_int32), C.c_int(n), _pp(preds), _ptr(indexes, C.c_uint32),
+           _ptr(npl, C.c_uint32), C.byref(cnt))
+    return preds, indexes, npl[:cnt.value].copy(), r
+
+
+def ref_lod_build(params, xyz):
+    load_ref().tmc13ref_lod_build.restype = C.c_double
+    p, i, n, t = _run_lod(load_ref().tmc13ref_lod_build, params, xyz)
+    return p, i, n
+
+
+def oracle_lod_build(params, xyz):
+    lib = load_oracle()
+    lib.oracle_lod_build.restype = C.c_int
+    p, i, n, r = _run_lod(lib.oracle_lod_build, params, xyz)
+    assert r == 0
+    return p, i, n

@@ -152,3 +152,60 @@ def test_live_lifting(a):
         ir = ref_lift(0, preds, qw_r, npl, fr)
         io = oracle_lift(0, preds, qw_o, npl, fo)
         assert np.array_equal(ir, io)
+
+
+LOD_CASES = [
+    dict(),
+    dict(distribution=0),
+    dict(decimation=1),
+    dict(decimation=2),
+    dict(decimation=0, skip_layers=0, intra_range=128, inter_range=128, blending=1),
+    dict(decimation=1, skip_layers=0, intra_range=16, inter_range=16, blending=1, period=3),
+    dict(decimation=2, k=1, inter_range=8),
+    dict(decimation=0, bias=(1, 2, 3), levels=6, dist2=1),
+]
+
+
+def _cmp_lod(xyz, kw):
+    lp = make_lod_params(**kw)
+    rp, ri, rn = ref_lod_build(lp, xyz)
+    op, oi, on = oracle_lod_build(lp, xyz)
+    assert np.array_equal(rn, on), kw
+    assert np.array_equal(ri, oi), kw
+    assert np.array_equal(rp, op), kw
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", LOD_CASES)
+def test_live_lod(kw):
+    """lod_oracle.c against AttributeLods::generate of the compiled reference:
+    numPointsInLod, indexes and every predictor (count, indices, weights)."""
+    xyz, _ = cloud_shell(40000, bits=9, seed=3)
+    _cmp_lod(xyz, kw)
+    xyz, _ = cloud_lidar(40000, seed=2)
+    _cmp_lod(xyz, dict(kw, levels=8))
+
+
+@needs_ref
+def test_live_lod_edge_cases():
+    xyz, _ = cloud_random(20000, 21, seed=5, dup_frac=0.1)   # many atlases, stalled fill cursor
+    _cmp_lod(xyz, dict(levels=14))
+    _cmp_lod(xyz, dict(decimation=1))
+    xyz, _ = cloud_random(20000, 5, seed=6)                  # heavy duplicates
+    for dec in (0, 1, 2):
+        _cmp_lod(xyz, dict(decimation=dec, levels=5))
+    for n in (1, 2, 5, 40):
+        xyz, _ = cloud_random(n, 4, seed=n)
+        _cmp_lod(xyz, dict())
+
+
+def test_lod_golden():
+    from golden.make_golden import LOD_GOLDEN_CASES
+
+    g = np.load(os.path.join(GOLD, "lod_golden.npz"))
+    for cname in ("shell", "sparse"):
+        for i, kw in enumerate(LOD_GOLDEN_CASES):
+            p, idx, npl = oracle_lod_build(make_lod_params(**kw), g[f"{cname}/xyz"])
+            assert np.array_equal(npl, g[f"{cname}/{i}/npl"])
+            assert np.array_equal(idx, g[f"{cname}/{i}/indexes"])
+            assert np.array_equal(p, g[f"{cname}/{i}/preds"])
