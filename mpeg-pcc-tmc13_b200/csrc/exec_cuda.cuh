@@ -366,6 +366,9 @@ struct DeviceExec {
     PCC_CUDA_CHECK(cudaStreamSynchronize(stream));
   }
 
+  // Morton keys + stable radix sort (defined in morton_sort.cuh)
+  void morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* order);
+
   template<class F>
   void foreach(int64_t n, const F& f)
   {

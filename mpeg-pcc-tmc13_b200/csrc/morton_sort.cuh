@@ -289,4 +289,10 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
   }
 }
 
+inline void
+DeviceExec::morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* order)
+{
+  device_morton_sort(*this, xyz, n, keys, order);
+}
+
 }  // namespace pccb200

@@ -18,6 +18,7 @@
 
 #include "exec_cuda.cuh"
 #include "lifting.cuh"
+#include "lod_pipeline.cuh"
 #include "morton_sort.cuh"
 #include "pcc_attr_b200.h"
 #include "raht_pipeline.cuh"
@@ -657,6 +658,29 @@ pccb200_profile_read(double ms_out[PCCB200_NUM_PHASES], uint64_t launches_out[PC
     ms_out[i] = c.profMs[i];
     launches_out[i] = c.profLaunches[i];
   }
+}
+
+int
+pccb200_lod_build(const pccb200_lod_params* params, const int32_t* xyz, int32_t n,
+                  pccb200_predictor* preds_out, uint32_t* indexes_out,
+                  uint32_t* num_points_in_lod_out, int32_t* lod_count_out)
+{
+  if (!params || !xyz || !preds_out || !indexes_out || !num_points_in_lod_out || !lod_count_out
+      || n <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    pccb200_predictor* dP = ex.alloc<pccb200_predictor>(n);
+    uint32_t* dIdx = ex.alloc<uint32_t>(n);
+    int cnt = 0;
+    int rc = lod_run(ex, *params, dXyz, n, dP, dIdx, num_points_in_lod_out, &cnt);
+    if (rc != PCCB200_OK)
+      return fail(rc, "invalid LoD parameters");
+    *lod_count_out = cnt;
+    to_host(ex, preds_out, dP, size_t(n));
+    to_host(ex, indexes_out, dIdx, size_t(n));
+    return PCCB200_OK;
+  });
 }
 
 int

@@ -50,6 +50,26 @@ class Predictor(C.Structure):
     ]
 
 
+MAX_LODS = 32
+
+
+class LodParams(C.Structure):
+    """pccb200_lod_params <- LoD fields of pcc::AttributeParameterSet (tmc3/hls.h:795-857)"""
+    _fields_ = [
+        ("num_detail_levels", C.c_int32),
+        ("lod_decimation_type", C.c_int32),
+        ("lod_sampling_period", C.c_int32 * MAX_LODS),
+        ("dist2", C.c_int32),
+        ("num_pred_nearest_neighbours", C.c_int32),
+        ("inter_lod_search_range", C.c_int32),
+        ("intra_lod_search_range", C.c_int32),
+        ("intra_lod_prediction_skip_layers", C.c_int32),
+        ("prediction_with_distribution", C.c_int32),
+        ("lod_neigh_bias", C.c_int32 * 3),
+        ("pred_weight_blending", C.c_int32),
+    ]
+
+
 PREDICTOR_DTYPE = np.dtype([("neighbor_count", "<u4"), ("predictor_index", "<u4", 3),
                             ("weight", "<u4", 3)])
 
@@ -59,7 +79,7 @@ EXPORTS = [
     "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
     "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
     "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
-    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_time_begin", "pccb200_time_end",
+    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_lod_build", "pccb200_time_begin", "pccb200_time_end",
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
 ]
@@ -269,3 +289,17 @@ def profile_read():
     ln = (C.c_uint64 * NUM_PHASES)()
     lib().pccb200_profile_read(ms, ln)
     return {PHASE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_PHASES)}
+
+
+def lod_build(params, xyz):
+    """-> (predictors[N] (PREDICTOR_DTYPE), indexes[N], num_points_in_lod[lods])"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    n = xyz.shape[0]
+    preds = np.zeros(n, dtype=PREDICTOR_DTYPE)
+    indexes = np.zeros(n, dtype=np.uint32)
+    npl = np.zeros(MAX_LODS, dtype=np.uint32)
+    cnt = C.c_int32(0)
+    _check(lib().pccb200_lod_build(C.byref(params), _p(xyz, C.c_int32), C.c_int32(n),
+                                   C.cast(preds.ctypes.data, C.POINTER(Predictor)),
+                                   _p(indexes, C.c_uint32), _p(npl, C.c_uint32), C.byref(cnt)))
+    return preds, indexes, npl[:cnt.value].copy()

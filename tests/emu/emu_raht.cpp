@@ -2,6 +2,7 @@
 // product (raht_core.cuh / raht_pipeline.cuh) compiled for the host and run
 // as loops (see exec_host.h).  Built by tests/emu/Makefile into libemu.so.
 #include "exec_host.h"
+#include "lod_pipeline.cuh"
 #include "raht_pipeline.cuh"
 
 extern "C" int
@@ -22,3 +23,14 @@ extern "C" int64_t emu_quantize(int qp, int64_t x) { return pccb200::make_quanti
 extern "C" int64_t emu_scale(int qp, int64_t x) { return pccb200::make_quantizer(qp).scale(x); }
 extern "C" int64_t emu_fixed_mul(int64_t a, int64_t b) { return pccb200::fx_mul(a, b); }
 extern "C" int64_t emu_div_approx(int64_t a, uint64_t b, int32_t s) { return pccb200::div_approx(a, b, s); }
+
+extern "C" int
+emu_lod_build(const pccb200_lod_params* lp, const int32_t* xyz, int n, pccb200_predictor* preds,
+              uint32_t* indexes, uint32_t* npl, int32_t* lodCount)
+{
+  HostExec ex;
+  int cnt = 0;
+  int rc = pccb200::lod_run(ex, *lp, xyz, n, preds, indexes, npl, &cnt);
+  *lodCount = cnt;
+  return rc;
+}

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "raht_core.cuh"
@@ -44,6 +45,20 @@ struct HostExec {
   {
     for (int64_t i = 0; i < n; i++)
       f(i);
+  }
+  void morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* order)
+  {
+    std::vector<int32_t> idx(n);
+    std::vector<int64_t> k(n);
+    for (int64_t i = 0; i < n; i++) {
+      idx[i] = int32_t(i);
+      k[i] = pccb200::morton_addr(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    }
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return k[a] < k[b]; });
+    for (int64_t i = 0; i < n; i++) {
+      keys[i] = k[idx[i]];
+      order[i] = idx[i];
+    }
   }
   template<class P, class E>
   void compact(int64_t n, const P& pred, const E& emit, int* total = nullptr)

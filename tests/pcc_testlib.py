@@ -421,3 +421,11 @@ def oracle_lod_build(params, xyz):
     p, i, n, r = _run_lod(lib.oracle_lod_build, params, xyz)
     assert r == 0
     return p, i, n
+
+
+def emu_lod_build(params, xyz):
+    lib = load_emu()
+    lib.emu_lod_build.restype = C.c_int
+    p, i, n, r = _run_lod(lib.emu_lod_build, params, xyz)
+    assert r == 0, r
+    return p, i, n

@@ -264,3 +264,56 @@ def test_whole_codec_bitstream(b200, tmp_path):
         rc, log = ch.decode(ch.B200_BIN, out["ref"][0], d_b200)
         assert rc == 0, log[-2000:]
         assert md5(d_ref) == md5(d_b200) == md5(out["ref"][1])
+
+
+def _as_lod(pb, lp):
+    return pb.LodParams.from_buffer_copy(bytes(lp))
+
+
+def test_lod_golden(b200):
+    from golden.make_golden import LOD_GOLDEN_CASES
+
+    g = np.load(os.path.join(GOLD, "lod_golden.npz"))
+    for cname in ("shell", "sparse"):
+        for i, kw in enumerate(LOD_GOLDEN_CASES):
+            p, idx, npl = b200.lod_build(_as_lod(b200, make_lod_params(**kw)), g[f"{cname}/xyz"])
+            assert np.array_equal(npl, g[f"{cname}/{i}/npl"]), (cname, i)
+            assert np.array_equal(idx, g[f"{cname}/{i}/indexes"]), (cname, i)
+            assert np.array_equal(p, g[f"{cname}/{i}/preds"]), (cname, i)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(distribution=0), dict(decimation=1), dict(decimation=2),
+    dict(decimation=0, skip_layers=0, intra_range=128, inter_range=128, blending=1),
+    dict(decimation=1, skip_layers=0, intra_range=16, inter_range=16, blending=1, period=3),
+    dict(decimation=2, k=1, inter_range=8), dict(decimation=0, bias=(1, 2, 3), levels=6, dist2=1)])
+def test_lod_vs_oracle(b200, kw):
+    """LoD build on the device (Morton sort, subsampling dataflow, the atlas /
+    window neighbour search, weights) against the oracle: numPointsInLod,
+    indexes and every predictor bit-exact."""
+    for xyz in (cloud_shell(150000, bits=10, seed=3)[0], cloud_lidar(100000, seed=2)[0],
+                cloud_random(30000, 21, seed=5, dup_frac=0.1)[0], cloud_random(20000, 5, seed=6)[0]):
+        lp = make_lod_params(**kw)
+        op, oi, on = oracle_lod_build(lp, xyz)
+        gp, gi, gn = b200.lod_build(_as_lod(b200, lp), xyz)
+        assert np.array_equal(gn, on)
+        assert np.array_equal(gi, oi)
+        assert np.array_equal(gp, op)
+
+
+def test_lifting_end_to_end(b200):
+    """LoD build -> quantisation weights -> forward lifting -> inverse lifting,
+    all on the device, against the oracle chain; inverse(forward(x)) == x."""
+    rng = np.random.default_rng(3)
+    xyz, rgb = cloud_shell(200000, bits=10, seed=12)
+    lp = make_lod_params(levels=12)
+    gp, gi, gn = b200.lod_build(_as_lod(b200, lp), xyz)
+    op, oi, on = oracle_lod_build(lp, xyz)
+    assert np.array_equal(gp, op) and np.array_equal(gi, oi) and np.array_equal(gn, on)
+    qw = b200.quant_weights(gp, gn)
+    assert np.array_equal(qw, oracle_quant_weights(op))
+    attrs = rgb[gi].astype(np.int64) << 8
+    fwd = b200.lift(True, gp, qw, gn, attrs)
+    assert np.array_equal(fwd, oracle_lift(1, op, qw, on, attrs))
+    inv = b200.lift(False, gp, qw, gn, fwd)
+    assert np.array_equal(inv, attrs)

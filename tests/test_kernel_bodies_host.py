@@ -74,3 +74,17 @@ def test_qp_structures_and_edges():
     _cmp(xyz, attrs, make_params(), make_qpset(qp=20))
     xyz = np.array([[0, 0, 0], [2**20, 2**20, 2**20], [2**20 + 1, 2**20, 2**20]], dtype=np.int32)
     _cmp(xyz, attrs[:3], make_params(thr0=0, thr1=0), make_qpset(qp=20))
+
+
+from test_oracle_vs_reference import LOD_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("kw", LOD_CASES)
+def test_lod_bodies(kw):
+    """lod_core.cuh / lod_pipeline.cuh (host build) against the LoD oracle"""
+    for xyz in (cloud_shell(20000, bits=8, seed=3)[0], cloud_lidar(20000, seed=2)[0],
+                cloud_random(8000, 21, seed=5, dup_frac=0.1)[0], cloud_random(5000, 4, seed=6)[0]):
+        lp = make_lod_params(**dict(kw, levels=8))
+        op, oi, on = oracle_lod_build(lp, xyz)
+        ep, ei, en = emu_lod_build(lp, xyz)
+        assert np.array_equal(on, en) and np.array_equal(oi, ei) and np.array_equal(op, ep)
