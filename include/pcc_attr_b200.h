@@ -270,6 +270,52 @@ int pccb200_lift_inverse(const pccb200_predictor* preds, const uint64_t* qw,
                          int32_t lod_count, int64_t* attrs_inout,
                          int32_t num_attrs);
 
+/* Lifting quantisation (+ last-component prediction) of the coefficients in
+ * predictor order: the per-coefficient arithmetic of
+ * tmc3/AttributeEncoder.cpp:1424-1473,1597-1625 and
+ * computeLastComponentPredictionCoeff (:1498-1539).  attrs_inout: N x A
+ * lifting coefficients in, reconstructed coefficients out.  values_out: N x A
+ * quantised values (what the reference hands to its entropy coder).
+ * lcp_coeffs_out: num_detail_levels entries (colour with lcp_enabled), may be
+ * NULL otherwise.  point_qp_offsets: N x 2 in predictor order, or NULL.
+ * qpset.fixed_point_qp_offset must carry the lifting offset (24,
+ * tmc3/quantization.cpp:160-163). */
+int pccb200_lift_quantize(const pccb200_qpset* qpset,
+                          const int32_t* point_qp_offsets, const uint64_t* qw,
+                          int32_t n, const uint32_t* num_points_in_lod,
+                          int32_t lod_count, int32_t num_detail_levels,
+                          int64_t* attrs_inout, int32_t num_attrs,
+                          int32_t lcp_enabled, int32_t* values_out,
+                          int8_t* lcp_coeffs_out);
+/* Decoder side (tmc3/AttributeDecoder.cpp:711-749,815-837): values -> coefficients. */
+int pccb200_lift_dequantize(const pccb200_qpset* qpset,
+                            const int32_t* point_qp_offsets, const uint64_t* qw,
+                            int32_t n, const uint32_t* num_points_in_lod,
+                            int32_t lod_count, int32_t num_detail_levels,
+                            const int32_t* values_in, int32_t num_attrs,
+                            const int8_t* lcp_coeffs, int64_t* attrs_out);
+
+/* The lifting attribute coder without its entropy coding, entirely on the
+ * device (AttributeEncoder::encode{Colors,Reflectances}Lift,
+ * tmc3/AttributeEncoder.cpp:1379-1494,1543-1648): LoD build, quantisation
+ * weights, forward lifting, LCP + quantisation, inverse lifting, clip.
+ * attrs_inout: N x A in input order, overwritten with the reconstruction.
+ * values_out: N x A in coding (predictor) order.  point_qp_offsets: input
+ * order or NULL.  lcp_coeffs_out: num_detail_levels entries or NULL. */
+int pccb200_attr_lift_encode(const pccb200_lod_params* lod,
+                             const pccb200_qpset* qpset, int32_t lcp_enabled,
+                             const int32_t* point_qp_offsets, const int32_t* xyz,
+                             int32_t* attrs_inout, int32_t num_attrs, int32_t n,
+                             int32_t bitdepth, int32_t* values_out,
+                             int8_t* lcp_coeffs_out);
+/* Decoder counterpart (AttributeDecoder::decode{Colors,Reflectances}Lift). */
+int pccb200_attr_lift_decode(const pccb200_lod_params* lod,
+                             const pccb200_qpset* qpset, int32_t lcp_enabled,
+                             const int32_t* point_qp_offsets, const int32_t* xyz,
+                             int32_t* attrs_out, int32_t num_attrs, int32_t n,
+                             int32_t bitdepth, const int32_t* values_in,
+                             const int8_t* lcp_coeffs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,189 @@ struct LiftUpdateApplyFn {
   }
 };
 
+//----------------------------------------------------------------------------
+// lifting quantisation + last-component prediction
+//   tmc3/AttributeEncoder.cpp:1424-1473,1498-1539,1597-1625
+//   tmc3/AttributeDecoder.cpp:711-749,815-837
+
+struct LodTable {
+  uint32_t npl[PCCB200_MAX_LODS];
+  int lodCount;
+  // level of detail of predictor i: number of cumulative sizes <= i
+  PCC_HD int lod_of(int64_t i) const
+  {
+    int l = 0;
+    while (l < lodCount && int64_t(npl[l]) <= i)
+      l++;
+    return l;
+  }
+};
+
+// per-LoD sums for computeLastComponentPredictionCoeff (note the reference's
+// truncation of the products to int)
+struct LcpSumFn {
+  const int64_t* coeffs;  // n*3
+  LodTable lt;
+  uint64_t* sums;  // [lod][2]: sum k1*k2, sum k1*k1 (two's complement)
+  PCC_HD void operator()(int64_t i) const
+  {
+    const uint64_t k1 = uint64_t(coeffs[i * 3 + 1]), k2 = uint64_t(coeffs[i * 3 + 2]);
+    const int32_t m12 = int32_t(uint32_t(k1 * k2));
+    const int32_t m11 = int32_t(uint32_t(k1 * k1));
+    const int l = lt.lod_of(i);
+    atomic_add_u64(&sums[2 * l], uint64_t(int64_t(m12)));
+    atomic_add_u64(&sums[2 * l + 1], uint64_t(int64_t(m11)));
+  }
+};
+
+struct LiftQuantFn {
+  int forward;
+  int A;
+  LayerQp layers[PCCB200_MAX_QP_LAYERS];
+  int numLayers;
+  LodTable lt;
+  int lcp[PCCB200_MAX_LODS + 1];
+  const int32_t* qpo;      // n*2 in predictor order, or null
+  const uint64_t* qw;
+  int64_t* attrs;          // n*A coefficients in / reconstructed coefficients out
+  int32_t* values;         // n*A quantised values (out when forward, in otherwise)
+  PCC_HD void operator()(int64_t i) const
+  {
+    const int l = lt.lod_of(i);
+    const int layer = l < numLayers - 1 ? l : numLayers - 1;
+    Quantizer q[2];
+    make_quantizers(layers[layer], qpo ? qpo[2 * i] : 0, qpo ? qpo[2 * i + 1] : 0, q);
+    const int64_t iqw = int64_t(irsqrt64(qw[i]));
+    const int64_t qwt = int64_t((qw[i] * uint64_t(iqw) + (uint64_t(1) << 39)) >> 40);
+    int64_t* a = &attrs[i * A];
+    int32_t* v = &values[i * A];
+    if (forward)
+      v[0] = int32_t(q[0].quantize(a[0] * qwt));
+    a[0] = div_exp2_round_half_inf(q[0].scale(v[0]) * iqw, 40);
+    if (A == 1)
+      return;
+    const int64_t c = lcp[l];
+    if (forward)
+      v[1] = int32_t(q[1].quantize(a[1] * qwt));
+    int64_t scaled = q[1].scale(v[1]);
+    a[1] = div_exp2_round_half_inf(scaled * iqw, 40);
+    if (forward)
+      a[2] -= (c * a[1]) >> 2;
+    scaled = (scaled * c) >> 2;
+    if (forward)
+      v[2] = int32_t(q[1].quantize(a[2] * qwt));
+    scaled += q[1].scale(v[2]);
+    a[2] = div_exp2_round_half_inf(scaled * iqw, 40);
+  }
+};
+
+// computeLastComponentPredictionCoeff from the per-LoD sums (host, tiny)
+inline void
+lcp_from_sums(const int64_t* sums, int lodCount, int numDetailLevels, int8_t* out)
+{
+  int lod = 0;
+  for (; lod < lodCount && lod < numDetailLevels; lod++) {
+    const int64_t s12 = sums[2 * lod], s11 = sums[2 * lod + 1];
+    int scale = 0;
+    if (s12 && s11) {
+      const int sign = ((s12 < 0) ^ (s11 < 0)) ? -1 : 1;
+      scale = int(((s12 << 2) + sign * (s11 >> 1)) / s11);
+    }
+    out[lod] = int8_t(scale < -8 ? -8 : (scale > 8 ? 8 : scale));
+  }
+  for (; lod < numDetailLevels; lod++)
+    out[lod] = lod ? out[lod - 1] : 0;
+}
+
+// attrs: n*A coefficients (executor memory).  lcpInOut: host array of
+// numDetailLevels entries; computed when forward && lcpEnabled, read when
+// !forward && lcpEnabled.
+template<class Exec>
+int
+run_lift_quant(Exec& ex, bool forward, const pccb200_qpset& qs, const int32_t* qpo,
+               const uint64_t* qw, int64_t n, const uint32_t* numPointsInLod, int lodCount,
+               int numDetailLevels, int64_t* attrs, int A, bool lcpEnabled, int8_t* lcpInOut,
+               int32_t* values)
+{
+  if (lodCount < 1 || lodCount > PCCB200_MAX_LODS || numDetailLevels < lodCount
+      || numDetailLevels > PCCB200_MAX_LODS || qs.num_layers < 1
+      || qs.num_layers > PCCB200_MAX_QP_LAYERS || (A != 1 && A != 3))
+    return PCCB200_ERR_INVALID_ARG;
+  ex.phase(5);
+  LiftQuantFn fn;
+  fn.forward = forward;
+  fn.A = A;
+  fn.numLayers = qs.num_layers;
+  for (int i = 0; i < qs.num_layers; i++) {
+    fn.layers[i].luma = qs.layers[i][0];
+    fn.layers[i].chromaOffset = qs.layers[i][1];
+    fn.layers[i].maxQp = qs.max_qp;
+    fn.layers[i].fixedPointQpOffset = qs.fixed_point_qp_offset;
+  }
+  fn.lt.lodCount = lodCount;
+  for (int l = 0; l < lodCount; l++)
+    fn.lt.npl[l] = numPointsInLod[l];
+  for (int l = 0; l <= PCCB200_MAX_LODS; l++)
+    fn.lcp[l] = 0;
+  if (lcpEnabled && A == 3) {
+    if (forward) {
+      uint64_t* dSums = ex.template alloc<uint64_t>(2 * PCCB200_MAX_LODS + 2);
+      ex.zero(dSums, (2 * PCCB200_MAX_LODS + 2) * sizeof(uint64_t));
+      ex.foreach(n, LcpSumFn{attrs, fn.lt, dSums});
+      int64_t sums[2 * PCCB200_MAX_LODS + 2];
+      ex.download(sums, dSums, sizeof(sums));
+      lcp_from_sums(sums, lodCount, numDetailLevels, lcpInOut);
+    }
+    for (int l = 0; l < numDetailLevels; l++)
+      fn.lcp[l] = lcpInOut[l];
+    fn.lcp[numDetailLevels] = lcpInOut[numDetailLevels - 1];
+  }
+  fn.qpo = qpo;
+  fn.qw = qw;
+  fn.attrs = attrs;
+  fn.values = values;
+  ex.foreach(n, fn);
+  return PCCB200_OK;
+}
+
+// predictor order <-> point order helpers of the attribute-level calls
+struct GatherAttrShiftFn {   // out[i] = in[indexes[i]] << 8
+  const int32_t* in;
+  const uint32_t* indexes;
+  int A;
+  int64_t* out;
+  PCC_HD void operator()(int64_t i) const
+  {
+    for (int k = 0; k < A; k++)
+      out[i * A + k] = int64_t(in[size_t(indexes[i]) * A + k]) << 8;
+  }
+};
+struct GatherQpoFn {
+  const int32_t* in;
+  const uint32_t* indexes;
+  int32_t* out;
+  PCC_HD void operator()(int64_t i) const
+  {
+    out[2 * i] = in[2 * size_t(indexes[i])];
+    out[2 * i + 1] = in[2 * size_t(indexes[i]) + 1];
+  }
+};
+struct ScatterReconFn {  // out[indexes[i]] = clip(divExp2RoundHalfInf(in[i], 8))
+  const int64_t* in;
+  const uint32_t* indexes;
+  int A;
+  int32_t clipMax;
+  int32_t* out;
+  PCC_HD void operator()(int64_t i) const
+  {
+    for (int k = 0; k < A; k++) {
+      int64_t v = div_exp2_round_half_inf(in[i * A + k], 8);
+      v = v < 0 ? 0 : (v > clipMax ? clipMax : v);
+      out[size_t(indexes[i]) * A + k] = int32_t(v);
+    }
+  }
+};
+
 // executor-generic drivers (numPointsInLod is a host array)
 
 template<class Exec>

@@ -18,6 +18,7 @@
 
 #include "exec_cuda.cuh"
 #include "lifting.cuh"
+#include "lift_pipeline.cuh"
 #include "lod_pipeline.cuh"
 #include "morton_sort.cuh"
 #include "pcc_attr_b200.h"
@@ -735,6 +736,113 @@ pccb200_lift_inverse(const pccb200_predictor* preds, const uint64_t* qw, int32_t
                      int64_t* attrs_inout, int32_t num_attrs)
 {
   return lift_common(false, preds, qw, n, num_points_in_lod, lod_count, attrs_inout, num_attrs);
+}
+
+static int
+lift_quant_common(bool forward, const pccb200_qpset* qpset, const int32_t* qpo,
+                  const uint64_t* qw, int32_t n, const uint32_t* npl, int32_t lodCount,
+                  int32_t numDetailLevels, int64_t* attrs, int32_t A, int32_t lcpEnabled,
+                  int32_t* values, int8_t* lcp)
+{
+  if (!qpset || !qw || !npl || !attrs || !values || n <= 0 || (lcpEnabled && A == 3 && !lcp))
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    uint64_t* dQw = to_device(ex, qw, size_t(n));
+    int32_t* dQpo = qpo ? to_device(ex, qpo, size_t(n) * 2) : nullptr;
+    int64_t* dA = forward ? to_device(ex, attrs, size_t(n) * A) : ex.alloc<int64_t>(size_t(n) * A);
+    int32_t* dV = forward ? ex.alloc<int32_t>(size_t(n) * A) : to_device(ex, values, size_t(n) * A);
+    int rc = run_lift_quant(ex, forward, *qpset, dQpo, dQw, n, npl, lodCount, numDetailLevels, dA,
+                            A, lcpEnabled != 0, lcp, dV);
+    if (rc != PCCB200_OK)
+      return fail(rc, "invalid lifting quantisation parameters");
+    to_host(ex, attrs, dA, size_t(n) * A);
+    if (forward)
+      to_host(ex, values, dV, size_t(n) * A);
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_lift_quantize(const pccb200_qpset* qpset, const int32_t* point_qp_offsets,
+                      const uint64_t* qw, int32_t n, const uint32_t* num_points_in_lod,
+                      int32_t lod_count, int32_t num_detail_levels, int64_t* attrs_inout,
+                      int32_t num_attrs, int32_t lcp_enabled, int32_t* values_out,
+                      int8_t* lcp_coeffs_out)
+{
+  return lift_quant_common(true, qpset, point_qp_offsets, qw, n, num_points_in_lod, lod_count,
+                           num_detail_levels, attrs_inout, num_attrs, lcp_enabled, values_out,
+                           lcp_coeffs_out);
+}
+
+int
+pccb200_lift_dequantize(const pccb200_qpset* qpset, const int32_t* point_qp_offsets,
+                        const uint64_t* qw, int32_t n, const uint32_t* num_points_in_lod,
+                        int32_t lod_count, int32_t num_detail_levels, const int32_t* values_in,
+                        int32_t num_attrs, const int8_t* lcp_coeffs, int64_t* attrs_out)
+{
+  return lift_quant_common(false, qpset, point_qp_offsets, qw, n, num_points_in_lod, lod_count,
+                           num_detail_levels, attrs_out, num_attrs, lcp_coeffs != nullptr,
+                           const_cast<int32_t*>(values_in), const_cast<int8_t*>(lcp_coeffs));
+}
+
+// the whole lifting attribute coder minus entropy coding, on the device
+static int
+attr_lift_common(bool forward, const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                 int32_t lcpEnabled, const int32_t* qpo, const int32_t* xyz, int32_t* attrs,
+                 int32_t A, int32_t n, int32_t bitdepth, int32_t* values, int8_t* lcp)
+{
+  if (!lod || !qpset || !xyz || !attrs || !values || n <= 0 || (A != 1 && A != 3)
+      || bitdepth < 1 || bitdepth > 16)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  int8_t lcpLocal[PCCB200_MAX_LODS + 1] = {};
+  if (!forward && lcpEnabled && A == 3) {
+    if (!lcp)
+      return fail(PCCB200_ERR_INVALID_ARG, "lcp coefficients missing");
+    for (int l = 0; l < lod->num_detail_levels && l < PCCB200_MAX_LODS; l++)
+      lcpLocal[l] = lcp[l];
+  }
+  int rc = with_device([&](DeviceExec& ex) -> int {
+    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    int32_t* dIn = forward ? to_device(ex, attrs, size_t(n) * A) : nullptr;
+    int32_t* dQpoIn = qpo ? to_device(ex, qpo, size_t(n) * 2) : nullptr;
+    int32_t* dV = forward ? ex.alloc<int32_t>(size_t(n) * A) : to_device(ex, values, size_t(n) * A);
+    int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+    int rc2 = attr_lift_run(ex, forward, *lod, *qpset, lcpEnabled != 0, dQpoIn, dXyz, dIn, dOut, A,
+                            n, bitdepth, dV, lcpLocal);
+    if (rc2 != PCCB200_OK)
+      return fail(rc2, rc2 == PCCB200_ERR_UNSUPPORTED
+                         ? "a predictor references its own level of detail"
+                         : "invalid lifting parameters");
+    to_host(ex, attrs, dOut, size_t(n) * A);
+    if (forward)
+      to_host(ex, values, dV, size_t(n) * A);
+    return PCCB200_OK;
+  });
+  if (rc == PCCB200_OK && forward && lcp)
+    for (int l = 0; l < lod->num_detail_levels && l < PCCB200_MAX_LODS; l++)
+      lcp[l] = lcpLocal[l];
+  return rc;
+}
+
+int
+pccb200_attr_lift_encode(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                         int32_t lcp_enabled, const int32_t* point_qp_offsets, const int32_t* xyz,
+                         int32_t* attrs_inout, int32_t num_attrs, int32_t n, int32_t bitdepth,
+                         int32_t* values_out, int8_t* lcp_coeffs_out)
+{
+  return attr_lift_common(true, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_inout,
+                          num_attrs, n, bitdepth, values_out, lcp_coeffs_out);
+}
+
+int
+pccb200_attr_lift_decode(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                         int32_t lcp_enabled, const int32_t* point_qp_offsets, const int32_t* xyz,
+                         int32_t* attrs_out, int32_t num_attrs, int32_t n, int32_t bitdepth,
+                         const int32_t* values_in, const int8_t* lcp_coeffs)
+{
+  return attr_lift_common(false, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_out,
+                          num_attrs, n, bitdepth, const_cast<int32_t*>(values_in),
+                          const_cast<int8_t*>(lcp_coeffs));
 }
 
 }  // extern "C"

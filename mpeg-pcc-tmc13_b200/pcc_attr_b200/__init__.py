@@ -79,7 +79,8 @@ EXPORTS = [
     "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
     "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
     "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
-    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_lod_build", "pccb200_time_begin", "pccb200_time_end",
+    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_lod_build", "pccb200_lift_quantize", "pccb200_lift_dequantize",
+    "pccb200_attr_lift_encode", "pccb200_attr_lift_decode", "pccb200_time_begin", "pccb200_time_end",
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
 ]
@@ -303,3 +304,35 @@ def lod_build(params, xyz):
                                    C.cast(preds.ctypes.data, C.POINTER(Predictor)),
                                    _p(indexes, C.c_uint32), _p(npl, C.c_uint32), C.byref(cnt)))
     return preds, indexes, npl[:cnt.value].copy()
+
+
+def attr_lift_encode(lod_params, qpset, xyz, attrs, lcp_enabled=0, bitdepth=8, qpoffs=None):
+    """-> (values [N,A] coding order, reconstruction [N,A] point order, lcp coefficients)"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    n, a = attrs.shape
+    values = np.zeros((n, a), dtype=np.int32)
+    lcp = np.zeros(MAX_LODS, dtype=np.int8)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    _check(lib().pccb200_attr_lift_encode(
+        C.byref(lod_params), C.byref(qpset), C.c_int32(lcp_enabled), _p(qpoffs, C.c_int32),
+        _p(xyz, C.c_int32), _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n), C.c_int32(bitdepth),
+        _p(values, C.c_int32), _p(lcp, C.c_int8)))
+    return values, attrs, lcp[:lod_params.num_detail_levels].copy()
+
+
+def attr_lift_decode(lod_params, qpset, xyz, values, lcp=None, bitdepth=8, qpoffs=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    values = np.ascontiguousarray(values, dtype=np.int32)
+    n, a = values.shape
+    attrs = np.zeros((n, a), dtype=np.int32)
+    l2 = None
+    if lcp is not None:
+        l2 = np.zeros(MAX_LODS, dtype=np.int8)
+        l2[:len(lcp)] = lcp
+    _check(lib().pccb200_attr_lift_decode(
+        C.byref(lod_params), C.byref(qpset), C.c_int32(1 if lcp is not None else 0),
+        _p(qpoffs, C.c_int32), _p(xyz, C.c_int32), _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n),
+        C.c_int32(bitdepth), _p(values, C.c_int32), _p(l2, C.c_int8)))
+    return attrs

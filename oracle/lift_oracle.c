@@ -101,3 +101,97 @@ oracle_lift(int forward, const pccb200_predictor* preds, const uint64_t* qw,
     }
   }
 }
+
+/* ---- lifting quantisation and last-component prediction -----------------
+ *   per-coefficient loop        tmc3/AttributeEncoder.cpp:1424-1473 (colour),
+ *                               :1597-1625 (reflectance); decoder
+ *                               tmc3/AttributeDecoder.cpp:711-749, 815-837
+ *   computeLastComponentPredictionCoeff   tmc3/AttributeEncoder.cpp:1498-1539
+ */
+static void
+lift_quantizers(const pccb200_qpset* qs, int layer, int off0, int off1, orc_quantizer q[2])
+{
+  int qp0 = qs->layers[layer][0] + off0;
+  if (qp0 < 4) qp0 = 4;
+  if (qp0 > qs->max_qp) qp0 = qs->max_qp;
+  int qp1 = qs->layers[layer][1] + off1 + qp0;
+  if (qp1 < 4) qp1 = 4;
+  if (qp1 > qs->max_qp) qp1 = qs->max_qp;
+  q[0] = orc_mkquant(qp0 + qs->fixed_point_qp_offset);
+  q[1] = orc_mkquant(qp1 + qs->fixed_point_qp_offset);
+}
+
+void
+oracle_lcp_coeffs(const int64_t* coeffs, int n, const uint32_t* npl, int lodCount,
+                  int numDetailLevels, int8_t* out)
+{
+  int64_t s12 = 0, s11 = 0;
+  int lod = 0;
+  for (int l = 0; l < numDetailLevels; l++)
+    out[l] = 0;
+  for (int i = 0; i < n; i++) {
+    int32_t mult = (int32_t)(uint32_t)((uint64_t)coeffs[3 * (size_t)i + 1] * (uint64_t)coeffs[3 * (size_t)i + 2]);
+    int32_t mult2 = (int32_t)(uint32_t)((uint64_t)coeffs[3 * (size_t)i + 1] * (uint64_t)coeffs[3 * (size_t)i + 1]);
+    s12 += mult;
+    s11 += mult2;
+    if (lod >= lodCount || (uint32_t)i != npl[lod] - 1)
+      continue;
+    int scale = 0;
+    if (s12 && s11) {
+      int sign = ((s12 < 0) ^ (s11 < 0)) ? -1 : 1;
+      scale = (int)(((s12 << 2) + sign * (s11 >> 1)) / s11);
+    }
+    s12 = s11 = 0;
+    out[lod] = (int8_t)(scale < -8 ? -8 : (scale > 8 ? 8 : scale));
+    lod++;
+  }
+  for (; lod < numDetailLevels; lod++)
+    out[lod] = lod ? out[lod - 1] : 0;
+}
+
+/* forward == 1: attrs in = lifting coefficients, values out, attrs out =
+ * reconstructed coefficients; forward == 0: values in, attrs out. */
+void
+oracle_lift_quant(int forward, const pccb200_qpset* qs, const int32_t* qpo, const uint64_t* qw,
+                  int n, const uint32_t* npl, int lodCount, int64_t* attrs, int A,
+                  const int8_t* lcp, int32_t* values)
+{
+  int quantLayer = 0, lod = 0;
+  int lcpCoeff = (lcp && A == 3) ? lcp[0] : 0;
+  for (int i = 0; i < n; i++) {
+    if (quantLayer < lodCount && (uint32_t)i == npl[quantLayer])
+      quantLayer = quantLayer + 1 < qs->num_layers ? quantLayer + 1 : qs->num_layers - 1;
+    if (lod < lodCount && (uint32_t)i == npl[lod]) {
+      lod++;
+      if (lcp && A == 3)
+        lcpCoeff = lcp[lod];
+    }
+    orc_quantizer q[2];
+    lift_quantizers(qs, quantLayer, qpo ? qpo[2 * i] : 0, qpo ? qpo[2 * i + 1] : 0, q);
+    const int64_t iqw = (int64_t)orc_irsqrt(qw[i]);
+    const int64_t qwt = (int64_t)((qw[i] * (uint64_t)iqw + (1ull << 39)) >> 40);
+    int64_t* a = &attrs[(size_t)i * A];
+    int32_t* v = &values[(size_t)i * A];
+    if (A == 1) {
+      if (forward)
+        v[0] = (int32_t)orc_quantize(q[0], a[0] * qwt);
+      a[0] = orc_div_exp2_half_inf(orc_scale(q[0], v[0]) * iqw, 40);
+      continue;
+    }
+    if (forward)
+      v[0] = (int32_t)orc_quantize(q[0], a[0] * qwt);
+    a[0] = orc_div_exp2_half_inf(orc_scale(q[0], v[0]) * iqw, 40);
+    if (forward)
+      v[1] = (int32_t)orc_quantize(q[1], a[1] * qwt);
+    int64_t scaled = orc_scale(q[1], v[1]);
+    a[1] = orc_div_exp2_half_inf(scaled * iqw, 40);
+    if (forward)
+      a[2] -= (lcpCoeff * a[1]) >> 2;
+    scaled *= lcpCoeff;
+    scaled >>= 2;
+    if (forward)
+      v[2] = (int32_t)orc_quantize(q[1], a[2] * qwt);
+    scaled += orc_scale(q[1], v[2]);
+    a[2] = orc_div_exp2_half_inf(scaled * iqw, 40);
+  }
+}

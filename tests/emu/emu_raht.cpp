@@ -2,6 +2,7 @@
 // product (raht_core.cuh / raht_pipeline.cuh) compiled for the host and run
 // as loops (see exec_host.h).  Built by tests/emu/Makefile into libemu.so.
 #include "exec_host.h"
+#include "lift_pipeline.cuh"
 #include "lod_pipeline.cuh"
 #include "raht_pipeline.cuh"
 
@@ -33,4 +34,26 @@ emu_lod_build(const pccb200_lod_params* lp, const int32_t* xyz, int n, pccb200_p
   int rc = pccb200::lod_run(ex, *lp, xyz, n, preds, indexes, npl, &cnt);
   *lodCount = cnt;
   return rc;
+}
+
+extern "C" int
+emu_attr_lift(int forward, const pccb200_lod_params* lod, const pccb200_qpset* qs, int lcpEnabled,
+              const int32_t* qpo, const int32_t* xyz, int32_t* attrs, int A, int n, int bitdepth,
+              int32_t* values, int8_t* lcp)
+{
+  HostExec ex;
+  int8_t lcpLocal[PCCB200_MAX_LODS + 1] = {};
+  if (!forward && lcp)
+    for (int l = 0; l < lod->num_detail_levels; l++)
+      lcpLocal[l] = lcp[l];
+  std::vector<int32_t> out(size_t(n) * A);
+  int rc = pccb200::attr_lift_run(ex, forward != 0, *lod, *qs, lcpEnabled != 0, qpo, xyz, attrs,
+                                  out.data(), A, n, bitdepth, values, lcpLocal);
+  if (rc)
+    return rc;
+  std::copy(out.begin(), out.end(), attrs);
+  if (forward && lcp)
+    for (int l = 0; l < lod->num_detail_levels; l++)
+      lcp[l] = lcpLocal[l];
+  return 0;
 }

@@ -429,3 +429,102 @@ def emu_lod_build(params, xyz):
     p, i, n, r = _run_lod(lib.emu_lod_build, params, xyz)
     assert r == 0, r
     return p, i, n
+
+
+# --------------------------------------------------------------------------
+# lifting quantisation / whole lifting encoder
+
+_liftref = None
+
+
+def liftref_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtmc13_lift.so"))
+
+
+def ref_lift_encode(lod_params, qpset, lcp_enabled, xyz, attrs, bitdepth=8):
+    """The reference's own lifting encoder (LoD build, weights, forward lifting,
+    quantisation (+LCP), reconstruction): -> (values [N,A] predictor order,
+    recon [N,A] input order, lcp coefficients)."""
+    global _liftref
+    if _liftref is None:
+        _liftref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtmc13_lift.so"))
+        _liftref.tmc13ref_lift_encode.restype = C.c_double
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32)
+    n, a = attrs.shape
+    values = np.zeros((n, a), dtype=np.int32)
+    recon = np.zeros((n, a), dtype=np.int32)
+    lcp = np.zeros(MAX_LODS, dtype=np.int8)
+    _liftref.tmc13ref_lift_encode(
+        C.byref(lod_params), C.byref(qpset), C.c_int(lcp_enabled), _ptr(xyz, C.c_int32),
+        _ptr(attrs, C.c_int32), C.c_int(n), C.c_int(a), C.c_int(bitdepth),
+        _ptr(values, C.c_int32), _ptr(recon, C.c_int32), _ptr(lcp, C.c_int8))
+    return values, recon, lcp[:lod_params.num_detail_levels].copy()
+
+
+def oracle_lcp_coeffs(coeffs, npl, num_detail_levels):
+    lib = load_oracle()
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int64)
+    out = np.zeros(num_detail_levels, dtype=np.int8)
+    lib.oracle_lcp_coeffs(_ptr(coeffs, C.c_int64), C.c_int(coeffs.shape[0]), _ptr(npl, C.c_uint32),
+                          C.c_int(len(npl)), C.c_int(num_detail_levels), _ptr(out, C.c_int8))
+    return out
+
+
+def oracle_lift_quant(forward, qpset, qw, npl, attrs, lcp=None, values=None, qpo=None):
+    lib = load_oracle()
+    a = np.ascontiguousarray(attrs, dtype=np.int64).copy()
+    n, A = a.shape
+    v = np.zeros((n, A), dtype=np.int32) if values is None else np.ascontiguousarray(values, dtype=np.int32).copy()
+    lib.oracle_lift_quant(C.c_int(1 if forward else 0), C.byref(qpset), _ptr(qpo, C.c_int32),
+                          _ptr(qw, C.c_uint64), C.c_int(n), _ptr(npl, C.c_uint32), C.c_int(len(npl)),
+                          _ptr(a, C.c_int64), C.c_int(A), _ptr(lcp, C.c_int8), _ptr(v, C.c_int32))
+    return a, v
+
+
+def finish_lift_recon(inv, bitdepth):
+    """divExp2RoundHalfInf(x, 8) then clip (tmc3/AttributeEncoder.cpp:1484-1493)"""
+    r = np.where(inv >= 0, (inv + 128) >> 8, -((128 - inv) >> 8))
+    return np.clip(r, 0, (1 << bitdepth) - 1).astype(np.int32)
+
+
+def oracle_lift_encode(lod_params, qpset, lcp_enabled, xyz, attrs, bitdepth=8):
+    """The oracle chain equivalent to the reference's lifting encoder."""
+    preds, indexes, npl = oracle_lod_build(lod_params, xyz)
+    qw = oracle_quant_weights(preds)
+    a = attrs[indexes].astype(np.int64) << 8
+    fwd = oracle_lift(1, preds, qw, npl, a)
+    lcp = None
+    if lcp_enabled and attrs.shape[1] == 3:
+        lcp = oracle_lcp_coeffs(fwd, npl, lod_params.num_detail_levels)
+    rec_coef, values = oracle_lift_quant(1, qpset, qw, npl, fwd, lcp=lcp)
+    inv = oracle_lift(0, preds, qw, npl, rec_coef)
+    out = np.zeros_like(attrs)
+    out[indexes] = finish_lift_recon(inv, bitdepth)
+    return values, out, (lcp if lcp is not None else np.zeros(lod_params.num_detail_levels, dtype=np.int8))
+
+
+def _attr_lift(fn, forward, lod_params, qpset, lcp_enabled, xyz, attrs, values, lcp, bitdepth, qpo=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    n, a = attrs.shape
+    if forward:
+        values = np.zeros((n, a), dtype=np.int32)
+        lcp = np.zeros(MAX_LODS, dtype=np.int8)
+    else:
+        values = np.ascontiguousarray(values, dtype=np.int32)
+        l2 = np.zeros(MAX_LODS, dtype=np.int8)
+        l2[:len(lcp)] = lcp
+        lcp = l2
+    r = fn(C.c_int(1 if forward else 0), C.byref(lod_params), C.byref(qpset), C.c_int(lcp_enabled),
+           _ptr(qpo, C.c_int32), _ptr(xyz, C.c_int32), _ptr(attrs, C.c_int32), C.c_int(a), C.c_int(n),
+           C.c_int(bitdepth), _ptr(values, C.c_int32), _ptr(lcp, C.c_int8))
+    assert r == 0, r
+    return values, attrs, lcp[:lod_params.num_detail_levels].copy()
+
+
+def emu_attr_lift(forward, lod_params, qpset, lcp_enabled, xyz, attrs, values=None, lcp=None, bitdepth=8):
+    lib = load_emu()
+    lib.emu_attr_lift.restype = C.c_int
+    return _attr_lift(lib.emu_attr_lift, forward, lod_params, qpset, lcp_enabled, xyz, attrs, values,
+                      lcp, bitdepth)

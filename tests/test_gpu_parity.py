@@ -317,3 +317,24 @@ def test_lifting_end_to_end(b200):
     assert np.array_equal(fwd, oracle_lift(1, op, qw, on, attrs))
     inv = b200.lift(False, gp, qw, gn, fwd)
     assert np.array_equal(inv, attrs)
+
+
+@pytest.mark.parametrize("a", [1, 3])
+def test_lifting_attribute_coder(b200, a):
+    """pccb200_attr_lift_encode / _decode (LoD build, weights, lifting, LCP +
+    quantisation, reconstruction, all on the device) against the oracle chain,
+    which tests/test_oracle_vs_reference.py pins to the reference's own
+    lifting encoder."""
+    for xyz, attrs in (cloud_shell(120000, bits=10, seed=7, a=a), cloud_lidar(80000, seed=4, a=a)):
+        for dec, lcp, qp in ((0, 1, 34), (1, 0, 16), (2, 1, 22)):
+            lp = make_lod_params(levels=10, decimation=dec)
+            qs = make_qpset(qp=qp, chroma_offset=-2 if a == 3 else 0, fixed_point_qp_offset=24,
+                            layers=[(qp, -2 if a == 3 else 0), (qp + 2, 0), (qp + 4, 1)])
+            ov, orr, ol = oracle_lift_encode(lp, qs, lcp, xyz, attrs)
+            q2 = b200.QpSet.from_buffer_copy(bytes(qs))
+            gv, gr, gl = b200.attr_lift_encode(_as_lod(b200, lp), q2, xyz, attrs, lcp_enabled=lcp)
+            assert np.array_equal(gv, ov) and np.array_equal(gr, orr)
+            if a == 3 and lcp:
+                assert np.array_equal(gl, ol)
+            gd = b200.attr_lift_decode(_as_lod(b200, lp), q2, xyz, ov, lcp=ol if (a == 3 and lcp) else None)
+            assert np.array_equal(gd, orr)

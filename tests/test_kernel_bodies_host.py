@@ -88,3 +88,21 @@ def test_lod_bodies(kw):
         op, oi, on = oracle_lod_build(lp, xyz)
         ep, ei, en = emu_lod_build(lp, xyz)
         assert np.array_equal(on, en) and np.array_equal(oi, ei) and np.array_equal(op, ep)
+
+
+@pytest.mark.parametrize("a", [1, 3])
+def test_lifting_coder_bodies(a):
+    """lift_pipeline.cuh (host build): the whole lifting attribute coder minus
+    entropy coding, encoder and decoder, against the oracle chain"""
+    xyz, attrs = cloud_shell(15000, bits=8, seed=7, a=a)
+    for dec, lcp, qp in ((0, 1, 34), (1, 0, 16), (2, 1, 22)):
+        lp = make_lod_params(levels=8, decimation=dec)
+        qs = make_qpset(qp=qp, chroma_offset=-2 if a == 3 else 0, fixed_point_qp_offset=24,
+                        layers=[(qp, -2 if a == 3 else 0), (qp + 2, 0), (qp + 4, 1)])
+        ov, orr, ol = oracle_lift_encode(lp, qs, lcp, xyz, attrs)
+        ev, er, el = emu_attr_lift(1, lp, qs, lcp, xyz, attrs)
+        assert np.array_equal(ev, ov) and np.array_equal(er, orr)
+        if a == 3 and lcp:
+            assert np.array_equal(el, ol)
+        _, dr, _ = emu_attr_lift(0, lp, qs, lcp, xyz, attrs * 0, values=ov, lcp=ol)
+        assert np.array_equal(dr, orr)

@@ -209,3 +209,29 @@ def test_lod_golden():
             assert np.array_equal(npl, g[f"{cname}/{i}/npl"])
             assert np.array_equal(idx, g[f"{cname}/{i}/indexes"])
             assert np.array_equal(p, g[f"{cname}/{i}/preds"])
+
+
+needs_liftref = pytest.mark.skipif(not liftref_available(),
+                                   reason="oracle/_ref/libtmc13_lift.so not built (make -C oracle liftref)")
+
+
+@needs_liftref
+@pytest.mark.parametrize("a", [1, 3])
+def test_live_lifting_encoder(a):
+    """The oracle chain (LoD build, weights, lifting, LCP, quantisation,
+    reconstruction) against the reference's own lifting encoder bodies
+    (encodeColorsLift / encodeReflectancesLift): quantised values as decoded
+    from the reference's arithmetic-coded payload, the reconstruction written
+    back into the point cloud, and the LCP coefficients."""
+    for cloud in (cloud_shell(20000, bits=9, seed=3, a=a), cloud_lidar(20000, seed=2, a=a)):
+        xyz, attrs = cloud
+        for qp in (34, 16):
+            for lcp in (0, 1):
+                for dec in (0, 1, 2):
+                    lp = make_lod_params(levels=10, decimation=dec)
+                    qs = make_qpset(qp=qp, chroma_offset=-2 if a == 3 else 0, fixed_point_qp_offset=24)
+                    rv, rr, rl = ref_lift_encode(lp, qs, lcp, xyz, attrs)
+                    ov, orr, ol = oracle_lift_encode(lp, qs, lcp, xyz, attrs)
+                    assert np.array_equal(rv, ov) and np.array_equal(rr, orr)
+                    if a == 3 and lcp:
+                        assert np.array_equal(rl, ol)
