@@ -270,8 +270,16 @@ run_lift_quant(Exec& ex, bool forward, const pccb200_qpset& qs, const int32_t* q
     fn.layers[i].maxQp = qs.max_qp;
     fn.layers[i].fixedPointQpOffset = qs.fixed_point_qp_offset;
   }
-  fn.lt.lodCount = lodCount;
-  for (int l = 0; l < lodCount; l++)
+  // The reference advances its per-LoD counters with `if (i == npl[lod]) lod++`
+  // (tmc3/AttributeEncoder.cpp:1429-1437,1514-1515): an empty level of detail
+  // (two equal cumulative sizes) is never stepped over, so only the strictly
+  // increasing prefix of the table takes effect.
+  int effCount = 0;
+  while (effCount < lodCount
+         && numPointsInLod[effCount] > (effCount ? numPointsInLod[effCount - 1] : 0u))
+    effCount++;
+  fn.lt.lodCount = effCount;
+  for (int l = 0; l < effCount; l++)
     fn.lt.npl[l] = numPointsInLod[l];
   for (int l = 0; l <= PCCB200_MAX_LODS; l++)
     fn.lcp[l] = 0;
@@ -282,7 +290,7 @@ run_lift_quant(Exec& ex, bool forward, const pccb200_qpset& qs, const int32_t* q
       ex.foreach(n, LcpSumFn{attrs, fn.lt, dSums});
       int64_t sums[2 * PCCB200_MAX_LODS + 2];
       ex.download(sums, dSums, sizeof(sums));
-      lcp_from_sums(sums, lodCount, numDetailLevels, lcpInOut);
+      lcp_from_sums(sums, effCount, numDetailLevels, lcpInOut);
     }
     for (int l = 0; l < numDetailLevels; l++)
       fn.lcp[l] = lcpInOut[l];

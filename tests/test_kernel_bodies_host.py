@@ -106,3 +106,18 @@ def test_lifting_coder_bodies(a):
             assert np.array_equal(el, ol)
         _, dr, _ = emu_attr_lift(0, lp, qs, lcp, xyz, attrs * 0, values=ov, lcp=ol)
         assert np.array_equal(dr, orr)
+
+
+def test_lifting_coder_empty_lods():
+    """empty levels of detail (equal cumulative sizes): the reference's
+    per-LoD counters stop advancing; must be reproduced"""
+    rng = np.random.default_rng(1)
+    xyz = (rng.integers(0, 1 << 12, size=(12000, 3)) * 8).astype(np.int32)
+    attrs = rng.integers(0, 256, size=(12000, 3)).astype(np.int32)
+    xyz2, attrs2 = cloud_lidar(60000, seed=4, a=3)
+    qs = make_qpset(qp=30, chroma_offset=-2, fixed_point_qp_offset=24, layers=[(30, -2), (32, 0), (34, 1)])
+    for x, a_, d2 in ((xyz, attrs, 0), (xyz, attrs, 2), (xyz2, attrs2, 0)):
+        lp = make_lod_params(levels=10, decimation=0, dist2=d2)
+        ov, orr, ol = oracle_lift_encode(lp, qs, 1, x, a_)
+        ev, er, el = emu_attr_lift(1, lp, qs, 1, x, a_)
+        assert np.array_equal(ev, ov) and np.array_equal(er, orr) and np.array_equal(el, ol)
