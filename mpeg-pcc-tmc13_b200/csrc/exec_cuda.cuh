@@ -25,6 +25,7 @@
 #include <atomic>
 #include <vector>
 
+#include "lod_subsample_warp.cuh"
 #include "raht_block_warp.cuh"
 
 namespace pccb200 {
@@ -420,6 +421,46 @@ struct DeviceExec {
     k_scan_tiles<<<1, 1024, 0, stream>>>(tiles, numTiles, total);
     k_tile_emit<P, E><<<numTiles, kTileThreads, 0, stream>>>(pred, emit, n, tiles);
     g_launchCount += 3;
+    PCC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // Distance subsampling over cells in Morton order (see lod_subsample_warp.cuh)
+  void subsample_distance(const SubsampleDistanceFn& fn, int nCells)
+  {
+    if (nCells <= 0)
+      return;
+    static const bool threadMode = [] {
+      const char* e = getenv("PCCB200_BLOCK_KERNEL");
+      return e && !strcmp(e, "thread");
+    }();
+    if (threadMode) {
+      ordered(nCells, fn);
+      return;
+    }
+    SubsampleCellsArgs a;
+    a.v = fn.v;
+    a.input = fn.input;
+    a.cellFirst = fn.cellFirst;
+    a.nCells = nCells;
+    a.shiftBits0 = fn.shiftBits0;
+    a.decision = fn.decision;
+    a.keep = fn.keep;
+    a.nb = alloc<int32_t>(size_t(nCells) * 19);
+    Scope sc(*this);
+    const int64_t threads = int64_t(nCells) * 19;
+    k_cell_neighbours<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(a);
+    PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    int64_t blocks = (int64_t(nCells) + 7) / 8;
+    const int inFlight = activeCalls ? activeCalls->load() : 1;
+    int64_t cap = int64_t(numSMs) * 8;
+    if (inFlight > 1)
+      cap /= 2 * inFlight;
+    if (cap < 8)
+      cap = 8;
+    if (blocks > cap)
+      blocks = cap;
+    k_subsample_cells<<<unsigned(blocks), 256, 0, stream>>>(a, ticket);
+    g_launchCount += 2;
     PCC_CUDA_CHECK(cudaGetLastError());
   }
 

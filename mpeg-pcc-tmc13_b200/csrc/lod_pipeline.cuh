@@ -111,6 +111,7 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
   for (int lod = 0; nInput > 0 && lod < L; lod++) {
     const int start = nIndexes;
     int nRet = 0, nQ = 0;
+    ex.phase(1);  // (profiling tag: subsampling)
     if (lod == L - 1 || nInput == 1 && cfg.decimation != 1) {
       // last level, or a single point left: everything is refined
       ex.foreach(nInput, CopyU32Fn{input, queries});
@@ -140,7 +141,7 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
         fn.shiftBits0 = cfg.dist2 + lod;
         fn.decision = decision;
         fn.keep = keep;
-        ex.ordered(nCells, fn);
+        ex.subsample_distance(fn, nCells);
       } else {
         ex.foreach(1, CentroidSegmentFn{cellFirst, nCells, nInput, cfg.samplingPeriod[lod],
                                         segFirst, dCount + 1});
@@ -158,6 +159,7 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
     nIndexes += nQ;
 
     // nearest neighbours of the refined points among the retained ones
+    ex.phase(2);  // (profiling tag: neighbour search)
     if (nQ > 0) {
       KnnFn kn;
       kn.cfg = cfg;
@@ -195,6 +197,7 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
     nInput = nRet;
   }
 
+  ex.phase(3);  // (profiling tag: finalisation)
   FinalizePredictorFn fin;
   fin.n = N;
   fin.blending = cfg.blending;

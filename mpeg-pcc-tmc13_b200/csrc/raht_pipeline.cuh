@@ -16,6 +16,7 @@
 //                                           e(rank, i) for every i with p(i),
 //                                           rank = number of j < i with p(j);
 //                                           *total (executor memory) = count
+//   void subsample_distance(SubsampleDistanceFn fn, int nCells)   (lod_pipeline.cuh)
 //   void block_stage(BlockFn fn, int64_t nBlocks, int* tzNext)
 //                                           one top-down stage; see exec_cuda.cuh
 //

@@ -70,6 +70,11 @@ struct HostExec {
     if (total)
       *total = int(rank);
   }
+  template<class Fn>
+  void subsample_distance(const Fn& fn, int nCells)
+  {
+    ordered(nCells, fn);
+  }
   // one top-down stage, in Morton order: single-child fast path (PrepFn), the
   // thread-per-block body for the rest, then the zero-run hand-over
   template<class Fn>
