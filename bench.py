@@ -432,6 +432,55 @@ def run_ours(args):
     h2d = F * (2 * xyz.nbytes + rgb.nbytes + refl.nbytes)
     d2h = F * 2 * (rgb.nbytes + refl.nbytes)
 
+    # ---- the lifting path (SURVEY.md 8d config 4 shape): LoD build + weights +
+    # lifting + quantisation + reconstruction of a dense 1M-point surface slice,
+    # host-pointer ABI, reported beside the headline (extra key, not `value`)
+    lifting = None
+    if rank == 0 and not args.no_lifting:
+        from pcc_attr_b200.synth import cloud_shell
+
+        lxyz, lrgb = cloud_shell(N_POINTS, bits=11, seed=40)
+        lp = pb.LodParams()
+        lp.num_detail_levels, lp.lod_decimation_type, lp.dist2 = 12, 0, 0
+        lp.num_pred_nearest_neighbours, lp.inter_lod_search_range = 3, 1100000
+        lp.intra_lod_search_range, lp.intra_lod_prediction_skip_layers = 0, 13
+        lp.prediction_with_distribution, lp.pred_weight_blending = 1, 0
+        for i in range(3):
+            lp.lod_neigh_bias[i] = 1
+        for i in range(32):
+            lp.lod_sampling_period[i] = 4
+        lq = pb.QpSet()
+        lq.num_layers, lq.max_qp, lq.fixed_point_qp_offset = 1, 51, 24
+        lq.layers[0][0], lq.layers[0][1] = QP, CHROMA_OFFSET
+        lf = 8
+        pb.attr_lift_encode(lp, lq, lxyz, lrgb, lcp_enabled=1)
+        t0 = time.perf_counter()
+        pb.attr_lift_encode(lp, lq, lxyz, lrgb, lcp_enabled=1)
+        single = time.perf_counter() - t0
+        run_jobs([lambda: pb.attr_lift_encode(lp, lq, lxyz, lrgb, lcp_enabled=1)] * lf)
+        t0 = time.perf_counter()
+        run_jobs([lambda: pb.attr_lift_encode(lp, lq, lxyz, lrgb, lcp_enabled=1)] * lf)
+        batch = time.perf_counter() - t0
+        lifting = {
+            "workload": "1M-point dense surface slice (11-bit), RGB, lifting transform, 12 LoDs, "
+                        "distance subsampling, k=3, qp 34, LCP on: LoD build + weights + forward "
+                        "lifting + quantisation + reconstruction, host-pointer ABI (H2D/D2H inside)",
+            "single_call_ms": 1e3 * single,
+            "mpoints_per_s_single": lxyz.shape[0] / single / 1e6,
+            "mpoints_per_s_8_in_flight": lf * lxyz.shape[0] / batch / 1e6,
+        }
+        liftref = os.path.join(ROOT, "oracle", "_ref", "libtmc13_lift.so")
+        if os.path.exists(liftref) and not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import pcc_testlib as tl
+
+            t0 = time.perf_counter()
+            tl.ref_lift_encode(tl.make_lod_params(levels=12), tl.make_qpset(
+                qp=QP, chroma_offset=CHROMA_OFFSET, fixed_point_qp_offset=24), 1, lxyz, lrgb)
+            lifting["cpu_reference_ms_one_core"] = 1e3 * (time.perf_counter() - t0)
+            lifting["cpu_reference_note"] = ("the reference's own encodeColorsLift on one host core "
+                                             "(includes its entropy coding)")
+
     if distributed:
         total_ms, e2e_s = reduce_timing([total_ms, e2e_s], dist, dev)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -484,6 +533,7 @@ def run_ours(args):
                         "not bandwidth bound; see DESIGN.md"},
             "phase_ms_per_frame_alone": {k: v[0] / prof_steps for k, v in prof.items()},
         }
+        line["lifting_path"] = lifting
         # reported CPU baseline: single N=1 run only (bounded: one frame)
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -509,6 +559,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lifting", action="store_true", help="skip the extra lifting-path measurement")
     ap.add_argument("--frames", type=int, default=16,
                     help="independent frames in flight per GPU per step (intra coding: frames "
                          "are independent work units)")
