@@ -569,7 +569,7 @@ struct DeviceExec {
       cap = 8;
     if (blocks > cap)
       blocks = cap;
-    {
+    if (experiment != 2) {  // (2: timing experiment without the dataflow kernel, WRONG RESULTS)
       Scope sc(*this);
       k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
     }
