@@ -27,6 +27,7 @@
 
 #include "lod_subsample_warp.cuh"
 #include "raht_block_warp.cuh"
+#include "raht_block_warp8.cuh"
 
 namespace pccb200 {
 
@@ -541,14 +542,25 @@ struct DeviceExec {
       g_launchCount++;
     }
     PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
+    // PCCB200_BLOCK_KERNEL=warp32 selects the one-block-per-warp kernel
+    // (raht_block_warp.cuh) instead of four blocks per warp, for A/B comparison
+    static const bool warp32 = [] {
+      const char* e = getenv("PCCB200_BLOCK_KERNEL");
+      return e && !strcmp(e, "warp32");
+    }();
     static int perSM = 0;
     if (!perSM) {
-      PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &perSM, k_block_warp, kWarpBlockThreads, 0));
+      if (warp32)
+        PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &perSM, k_block_warp, kWarpBlockThreads, 0));
+      else
+        PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &perSM, k_block_warp8, kWarpBlockThreads, 0));
       if (perSM < 1)
         perSM = 1;
     }
-    const int64_t perCta = int64_t(kWarpBlockThreads / 32) * kWarpBlockChunk;
+    const int64_t perCta =
+      int64_t(kWarpBlockThreads / 32) * (warp32 ? kWarpBlockChunk : kGroupsPerWarp);
     int64_t blocks = (nBlocks + perCta - 1) / perCta;
     // calls in flight share the machine: the persistent grid of each takes
     // its part (sampled at launch time)
@@ -571,7 +583,10 @@ struct DeviceExec {
       blocks = cap;
     if (experiment != 2) {  // (2: timing experiment without the dataflow kernel, WRONG RESULTS)
       Scope sc(*this);
-      k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
+      if (warp32)
+        k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
+      else
+        k_block_warp8<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
     }
     g_launchCount++;
     PCC_CUDA_CHECK(cudaGetLastError());

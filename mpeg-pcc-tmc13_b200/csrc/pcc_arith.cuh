@@ -117,6 +117,28 @@ div_exp2_round_half_inf_u(uint64_t x, int shift)
   return shift ? ((uint64_t(1) << (shift - 1)) + x) >> shift : x;
 }
 
+// Small lookup tables indexed at run time: a local array would be rebuilt on
+// the stack of every device thread, so device code reads a __constant__ copy.
+//   PCC_TABLE(uint8_t, kFoo, 3, {1, 2, 3})   defines   kFoo(i)
+#if defined(__CUDACC__)
+#  define PCC_TABLE(type, name, n, ...) \
+    static const type name##_host[n] = __VA_ARGS__; \
+    static __device__ __constant__ type name##_dev[n] = __VA_ARGS__; \
+    PCC_HD type name(int i) \
+    { \
+      PCC_TABLE_BODY(name) \
+    }
+#  if defined(__CUDA_ARCH__)
+#    define PCC_TABLE_BODY(name) return name##_dev[i];
+#  else
+#    define PCC_TABLE_BODY(name) return name##_host[i];
+#  endif
+#else
+#  define PCC_TABLE(type, name, n, ...) \
+    static const type name##_host[n] = __VA_ARGS__; \
+    PCC_HD type name(int i) { return name##_host[i]; }
+#endif
+
 //----------------------------------------------------------------------------
 // inverse square root: 96-entry seed, two Newton iterations.  The seed tables
 // are normative constants of the G-PCC specification.
@@ -241,18 +263,19 @@ struct Quantizer {
   PCC_HD int64_t scale(int64_t x) const { return x * step; }
 };
 
+// kQpStep / kQpStepRecip, tmc3/tables.cpp:478-481
+PCC_TABLE(int32_t, kQpStep, 6, {161, 181, 203, 228, 256, 287})
+PCC_TABLE(int32_t, kQpStepRecip, 6, {416825, 370767, 330586, 294337, 262144, 233829})
+
 PCC_HD Quantizer
 make_quantizer(int qp)
 {
-  // kQpStep / kQpStepRecip, tmc3/tables.cpp:478-481
-  const int32_t kStep[6] = {161, 181, 203, 228, 256, 287};
-  const int32_t kRecip[6] = {416825, 370767, 330586, 294337, 262144, 233829};
   qp = qp < 4 ? 4 : qp;
   int sh = qp / 6;
   int r = qp - 6 * sh;
   Quantizer q;
-  q.step = kStep[r] << sh;
-  q.recip = kRecip[r] >> sh;
+  q.step = kQpStep(r) << sh;
+  q.recip = kQpStepRecip(r) >> sh;
   return q;
 }
 

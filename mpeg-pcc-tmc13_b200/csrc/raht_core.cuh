@@ -307,22 +307,22 @@ scale_rsqrt(int64_t v, int w)
 }
 
 // RDOQ: cost in bits of a zero run of length tz (RAHT.cpp:1619-1632)
+PCC_TABLE(uint8_t, kZeroRunBins, 11, {1, 2, 3, 5, 5, 7, 7, 9, 9, 11, 11})
 PCC_HD int
 zero_run_rate(int tz)
 {
-  const int kBins[11] = {1, 2, 3, 5, 5, 7, 7, 9, 9, 11, 11};
   if (tz <= 10)
-    return kBins[tz];
+    return kZeroRunBins(tz);
   int a = 32 - clz32(uint32_t(tz - 10));
   return 11 + 2 * a - 1 + 2;
 }
 
+PCC_TABLE(int16_t, kLutLog, 16,
+          {0, 256, 406, 512, 594, 662, 719, 768, 812, 850, 886, 918, 947, 975, 1000, 1024})
 PCC_HD int
 lut_log(int64_t aq)
 {
-  const int kLog[16] = {0,   256, 406, 512, 594, 662, 719,  768,
-                        812, 850, 886, 918, 947, 975, 1000, 1024};
-  return kLog[aq < 15 ? int(aq) : 15];
+  return kLutLog(aq < 15 ? int(aq) : 15);
 }
 
 // A reconstruction slot that has not been written yet at the current stage
@@ -341,23 +341,14 @@ PCC_HD int tz_value(int w) { return w >> 2; }
 
 
 // tables of findNeighbours / intraDcPred (RAHT.cpp:314-326,375-377,438-440)
-PCC_HD int neigh_mask(int i)
-{
-  const uint8_t k[19] = {255, 240, 204, 170, 192, 160, 136, 3, 5, 15,
-                         17,  51,  85,  10,  34,  12,  68,  48, 80};
-  return k[i];
-}
-PCC_HD int neigh_offset(int i)
-{
-  const uint8_t k[19] = {0, 35, 21, 14, 49, 42, 28, 1,  2, 3,
-                         4, 5,  6,  10, 12, 17, 20, 33, 34};
-  return k[i];
-}
-PCC_HD int occu_shift(int i)
-{
-  const uint8_t k[12] = {6, 5, 4, 3, 2, 1, 3, 1, 2, 1, 2, 3};
-  return k[i];
-}
+PCC_TABLE(uint8_t, kNeighMask, 19,
+          {255, 240, 204, 170, 192, 160, 136, 3, 5, 15, 17, 51, 85, 10, 34, 12, 68, 48, 80})
+PCC_TABLE(uint8_t, kNeighOffset, 19,
+          {0, 35, 21, 14, 49, 42, 28, 1, 2, 3, 4, 5, 6, 10, 12, 17, 20, 33, 34})
+PCC_TABLE(uint8_t, kOccuShift, 12, {6, 5, 4, 3, 2, 1, 3, 1, 2, 1, 2, 3})
+PCC_HD int neigh_mask(int i) { return kNeighMask(i); }
+PCC_HD int neigh_offset(int i) { return kNeighOffset(i); }
+PCC_HD int occu_shift(int i) { return kOccuShift(i); }
 
 // index in parent stage P of neighbour i (1..18) of parent p, or -1: the node
 // must exist and lie within searchRange entries of p (findNeighbour,

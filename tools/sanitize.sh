@@ -16,7 +16,7 @@ orec, ocoef = oracle_raht(1, params, qpset, mort, a_s)
 assert np.array_equal(coef, ocoef) and np.array_equal(dec, rec)
 print("sanitizer run: results exact")
 PY
-for tool in memcheck racecheck; do
+for tool in ${TOOLS:-memcheck racecheck}; do
   echo "== compute-sanitizer --tool $tool"
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san.py 2>&1 | tail -6
 done
