@@ -27,7 +27,6 @@
 
 #include "lod_subsample_warp.cuh"
 #include "raht_block_warp.cuh"
-#include "raht_block_warp8.cuh"
 
 namespace pccb200 {
 
@@ -534,6 +533,13 @@ struct DeviceExec {
     upload(dRegions + numRegions, &hr, sizeof(TzRegion));
     numRegions++;
     a.regions = dRegions;
+    a.words = hr.words;
+    a.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+    static const int pollNs = [] {
+      const char* e = getenv("PCCB200_POLL_NS");
+      return e ? atoi(e) : 32;
+    }();
+    a.pollNs = pollNs;
     a.geom = nullptr;
     if (!root && fn.predInLvl) {
       a.geom = alloc<int32_t>(size_t(nBlocks) * kGeomStride);
@@ -542,25 +548,14 @@ struct DeviceExec {
       g_launchCount++;
     }
     PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
-    // PCCB200_BLOCK_KERNEL=warp32 selects the one-block-per-warp kernel
-    // (raht_block_warp.cuh) instead of four blocks per warp, for A/B comparison
-    static const bool warp32 = [] {
-      const char* e = getenv("PCCB200_BLOCK_KERNEL");
-      return e && !strcmp(e, "warp32");
-    }();
     static int perSM = 0;
     if (!perSM) {
-      if (warp32)
-        PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &perSM, k_block_warp, kWarpBlockThreads, 0));
-      else
-        PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &perSM, k_block_warp8, kWarpBlockThreads, 0));
+      PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &perSM, k_block_warp, kWarpBlockThreads, 0));
       if (perSM < 1)
         perSM = 1;
     }
-    const int64_t perCta =
-      int64_t(kWarpBlockThreads / 32) * (warp32 ? kWarpBlockChunk : kGroupsPerWarp);
+    const int64_t perCta = int64_t(kWarpBlockThreads / 32) * kWarpBlockChunk;
     int64_t blocks = (nBlocks + perCta - 1) / perCta;
     // calls in flight share the machine: the persistent grid of each takes
     // its part (sampled at launch time)
@@ -569,8 +564,12 @@ struct DeviceExec {
     // occupy every register file, or the short kernels of the other calls
     // (sort, tree build, PrepFn ...) queue behind them: leave half the machine.
     int64_t cap = int64_t(numSMs) * perSM;
+    static const int capShare = [] {  // percent of the machine all calls in flight may hold
+      const char* e = getenv("PCCB200_BLOCK_SHARE");
+      return e ? atoi(e) : 50;
+    }();
     if (inFlight > 1)
-      cap /= 2 * inFlight;
+      cap = cap * capShare / (100 * inFlight);
     static const int envCap = [] {
       const char* e = getenv("PCCB200_BLOCK_GRID");
       return e ? atoi(e) : 0;
@@ -583,10 +582,7 @@ struct DeviceExec {
       blocks = cap;
     if (experiment != 2) {  // (2: timing experiment without the dataflow kernel, WRONG RESULTS)
       Scope sc(*this);
-      if (warp32)
-        k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
-      else
-        k_block_warp8<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
+      k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
     }
     g_launchCount++;
     PCC_CUDA_CHECK(cudaGetLastError());

@@ -41,12 +41,14 @@ struct WarpBlockArgs {
   int experiment;           // timing experiments only (PCCB200_EXPERIMENT), 0 in production
   const struct TzRegion* regions;  // zero-run words/lists of every stage so far
   int stageIdx;                    // index of this stage in regions (0 = root)
+  int* words;                      // regions[stageIdx].words / .lists (kernel parameters:
+  unsigned long long* lists;       //   no load on the critical path)
+  int pollNs;                      // sleep between polls of a value still being produced
 };
 
 // Zero-run bookkeeping of one stage, indexed by worklist rank t:
-// words[t + 1] is block t's state word, lists[(t + 1) * 8 + i] its i-th
-// coefficient in scan order (0: never resets the run, a > 0: resets it unless
-// the run before it is at least a long).
+// words[t + 1] is block t's state word, 64-bit word t + 1 of lists the
+// classification of its coefficients in scan order (6-bit codes, see below).
 struct TzRegion {
   int* words;
   int* lists;
@@ -56,6 +58,9 @@ struct TzRegion {
 constexpr int kTzClassified = 3;  // word status: list published, outcome pending
 
 constexpr int kWarpBlockThreads = 256;
+#ifndef PCCB200_BLOCK_MIN_CTAS
+#  define PCCB200_BLOCK_MIN_CTAS 3  // resident CTAs per SM the block kernel is compiled for
+#endif
 constexpr int kWarpBlockChunk = 1;  // blocks claimed per ticket (consecutive blocks in one
                                     // warp would serialise the zero-run look-back chain)
 constexpr int kGeomStride = 20;     // ints per block: 19 neighbour indices + count
@@ -136,71 +141,92 @@ poll_rec(const int64_t* p)
   return v;
 }
 
-// RDOQ threshold of a coefficient: the smallest zero-run length tz for which
-// the reference's test (RAHT.cpp:1617-1636)
-//     (Dist2 << 26) < lambda * (Rate(tz) + ((Ratecoeff + 128) >> 8))
-// holds.  Rate(tz) is a non-decreasing step function; it changes at
-// tz = 0,1,2,3,5,7,9 and at tz = 10 + 2^(a-1), a >= 1.  INT_MAX: never.
+// RDOQ classification of a coefficient, 6 bits; eight of them, in scan order,
+// make the list a block publishes (TzRegion::lists, one 64-bit word per block):
+//   0      all components quantise to zero: never resets the run
+//   1      RDOQ removes it whatever the run length: never resets either
+//   2      always resets the run (sum |q| >= 3, or RDOQ never fires)
+//   3..8   removed if the run before it is at least 1,2,3,5,7,9 long
+//   8 + a  removed if the run before it is at least 10 + 2^(a-1), a = 1..30
+constexpr int kCodeZero = 0;
+constexpr int kCodeRemoved = 1;
+constexpr int kCodeHard = 2;
+
 __device__ __forceinline__ int
-rdoq_threshold(int64_t dist2, int64_t lambda, int rateCoeff)
+thr_decode(int code)  // code >= 3
+{
+  return code < 9 ? int((0x975321u >> (4 * (code - 3))) & 15u) : 10 + (1 << (code - 9));
+}
+
+// The smallest zero-run length tz for which the reference's test
+// (RAHT.cpp:1617-1636)
+//     (Dist2 << 26) < lambda * (Rate(tz) + ((Ratecoeff + 128) >> 8))
+// holds, as a code.  Rate(tz) (zero_run_rate) is a non-decreasing step
+// function: it changes at tz = 0,1,2,3,5,7,9 and at tz = 10 + 2^(a-1), a >= 1.
+__device__ __forceinline__ int
+rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 {
   const int64_t lhs = dist2 << 26;
   const int rc = (rateCoeff + 128) >> 8;
-  const int kTz[7] = {0, 1, 2, 3, 5, 7, 9};
+  const int kRate[7] = {1, 2, 3, 5, 7, 9, 11};  // zero_run_rate of 0,1,2,3,5,7,9
 #pragma unroll
   for (int i = 0; i < 7; i++)
-    if (lhs < lambda * (zero_run_rate(kTz[i]) + rc))
-      return kTz[i];
-  for (int a = 1; a <= 30; a++) {
-    const int tz = 10 + (1 << (a - 1));
-    if (lhs < lambda * (zero_run_rate(tz) + rc))
-      return tz;
-  }
-  return 0x7fffffff;
+    if (lhs < lambda * (kRate[i] + rc))
+      return i == 0 ? kCodeRemoved : 2 + i;
+  if (lhs >= lambda * (72 + rc))  // zero_run_rate(10 + 2^29) = 72
+    return kCodeHard;
+  for (int a = 1; a <= 30; a++)
+    if (lhs < lambda * (12 + 2 * a + rc))  // zero_run_rate(10 + 2^(a-1))
+      return 8 + a;
+  return kCodeHard;
 }
 
 // Is the run of non-resetting coefficients that ends just before block t of
-// stage a.stageIdx at least A long?  Walks back over the published
+// stage a.stageIdx at least `need` long?  Walks back over the published
 // classification of earlier blocks (this stage, then earlier stages); waits
 // only for blocks that have not classified their coefficients yet, never for
-// another block's own answer.  All lanes execute it uniformly.
+// another block's own answer (whatever a block publishes later is consistent
+// with its list, so lanes that observe different words still agree).
 __device__ __forceinline__ bool
-tz_run_at_least(const WarpBlockArgs& a, int t, int A)
+tz_run_at_least(const WarpBlockArgs& a, int t, int need)
 {
-  if (A <= 0)
+  if (need <= 0)
     return true;
-  int req = A;   // positions 1..req behind the block must not reset the run
-  int acc = 0;   // positions already verified
+  int req = need;  // positions 1..req behind the block must not reset the run
+  int acc = 0;     // positions already verified
   int s = a.stageIdx;
-  const TzRegion* rg = &a.regions[s];
+  const int* words = a.words;
+  const unsigned long long* lists = a.lists;
   int u = t - 1;
   for (;;) {
     if (u < 0) {
       if (--s < 0)
         return acc >= req;  // start of the call: the counter starts at 0
-      rg = &a.regions[s];
-      u = *rg->count - 1;
+      const TzRegion rg = a.regions[s];
+      words = rg.words;
+      lists = reinterpret_cast<const unsigned long long*>(rg.lists);
+      u = *rg.count - 1;
       continue;
     }
     int w;
-    while (tz_status(w = ld_acquire(&rg->words[u + 1])) == kTzNone)
-      __nanosleep(40);
+    while (tz_status(w = ld_acquire(&words[u + 1])) == kTzNone)
+      __nanosleep(a.pollNs);
     const int st = tz_status(w), v = tz_value(w);
     if (st == kTzExit)
       return v + acc >= req;
     if (st == kTzClassified) {
-      const int4 l0 = *reinterpret_cast<const int4*>(&rg->lists[size_t(u + 1) * 8]);
-      const int4 l1 = *reinterpret_cast<const int4*>(&rg->lists[size_t(u + 1) * 8 + 4]);
-      const int li[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-      for (int i = 7; i >= 0; i--)
-        if (i < v) {
-          const int pos = acc + (v - i);
-          if (pos > req)
-            return true;
-          if (li[i] > 0 && pos + li[i] > req)
-            req = li[i] >= 0x40000000 ? 0x7fffffff : pos + li[i];
+      const unsigned long long L = lists[u + 1];
+      for (int i = v - 1; i >= 0; i--) {
+        const int pos = acc + (v - i);
+        if (pos > req)
+          return true;
+        const int code = int((L >> (6 * i)) & 63);
+        if (code >= 3) {
+          const int li = thr_decode(code);
+          if (pos + li > req)
+            req = pos + li;
         }
+      }
     }
     acc += v;
     if (acc >= req)
@@ -209,7 +235,14 @@ tz_run_at_least(const WarpBlockArgs& a, int t, int A)
   }
 }
 
-// processes block p (worklist rank t); called by all 32 lanes
+// processes block p (worklist rank t); called by all 32 lanes.
+//
+// A block's latency is what bounds a stage (blocks wait for the
+// reconstruction of earlier neighbours), so the order of work is: first issue
+// every load that does not depend on blocks in flight (the block's own nodes,
+// the parent-stage values of all 19 neighbours fetched by 19 lanes at once,
+// quantisers, the inherited DC), do all the arithmetic that needs only those,
+// and only then look at the values still being produced.
 __device__ __forceinline__ void
 warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
 {
@@ -224,6 +257,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   const bool haar = cfg.haar != 0;
   const bool ext = cfg.ext != 0;
   const bool enc = cfg.isEncoder != 0;
+  const bool rdoq = enc && !haar;
 
   const int c0 = root ? 0 : P.first[p];
   uint32_t occ;
@@ -235,6 +269,42 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   }
   const bool present = (occ >> j) & 1;
   const int cidx = c0 + __popc(occ & ((1u << j) - 1));
+
+  //-- prediction gating: neighbour indices and count come from k_block_geom;
+  //   lane i < 19 fetches what the prediction needs of neighbour i
+  bool enablePred = false;
+  int64_t nv0 = 0, nv1 = 0, nv2 = 0;  // its reconstruction at the parent stage
+  uint32_t nocc = 0;                  // its occupancy, if its children may be used
+  int nfirst = 0;                     // and its first child
+  uint32_t validMask = 0;             // neighbours that contribute
+  if (a.predInLvl) {
+    const int g = lane < kGeomStride ? a.geom[size_t(t) * kGeomStride + lane] : -1;
+    const int count = __shfl_sync(0xffffffffu, g, 19);
+    const int nq = lane < 19 ? g : -1;
+    enablePred = count >= cfg.thr1 && __shfl_sync(0xffffffffu, g, 0) >= 0;
+    if (enablePred) {
+      const int parentOnly = cfg.subnode ? 7 : 19;
+      if (nq >= 0) {
+        nv0 = P.rec[size_t(nq) * A];
+        if (A > 1)
+          nv1 = P.rec[size_t(nq) * A + 1];
+        if (A > 2)
+          nv2 = P.rec[size_t(nq) * A + 2];
+        if (lane >= parentOnly && nq < p) {
+          nocc = P.occ[nq];
+          nfirst = P.first[nq];
+        }
+      }
+      // neighbours whose first component is out of range of the block's own
+      // parent are ignored (RAHT.cpp:392-404)
+      const int64_t self = shfl_i64(nv0, 0);
+      const int64_t limLow = 2 * self, limHigh = 25 * self;
+      const bool ok = nq >= 0 && (lane == 0 || (10 * nv0 > limLow && 10 * nv0 < limHigh));
+      validMask = __ballot_sync(0xffffffffu, ok);
+    }
+  }
+
+  //-- the block's own nodes
   const int w0 = present ? S.weight[cidx] : 0;
   int nodeQp0 = 0, nodeQp1 = 0;
   if (cfg.hasQp) {
@@ -251,6 +321,28 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   int64_t buf = 0;
   if (enc && act && present)
     buf = fx_from_int(S.attr[size_t(cidx) * A + k]);
+  int64_t dc = 0;  // inherited from the parent (RAHT.cpp:1726-1733)
+  if (!root && j == 0 && act)
+    dc = P.recUs[size_t(p) * A + k];
+  if (!a.predInLvl && root && present && k == 0)
+    S.nn[cidx] = 19;
+
+  //-- quantisers of coefficient j (the encoder never reaches this kernel with
+  //   AC qp offsets, so the RDOQ test and the quantisation share them)
+  Quantizer qz[2];
+  {
+    LayerQp lq;
+    lq.luma = a.qt->layers[a.qpLayer][0];
+    lq.chromaOffset = a.qt->layers[a.qpLayer][1];
+    lq.maxQp = cfg.maxQp;
+    lq.fixedPointQpOffset = cfg.fixedPointQpOffset;
+    int off0 = nodeQp0, off1 = nodeQp1;
+    if (j && a.acLayer < cfg.numAcLayers) {
+      off0 += a.qt->acQps[a.acLayer][j - 1][0];
+      off1 += a.qt->acQps[a.acLayer][j - 1][1];
+    }
+    make_quantizers(lq, off0, off1, qz);
+  }
 
   //-- weight tree and butterfly constants (mkWeightTree + RahtKernel)
   Bfly bf[3];
@@ -286,18 +378,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     rsMul = int64_t(irsqrt64(uint64_t(w0)) >> (40 - rsShift - kFracBits));
   }
 
-  //-- prediction gating: neighbour indices and count come from k_block_geom
-  bool enablePred = false;
-  int pidxLane = -1;
-  if (a.predInLvl) {
-    const int g = lane < kGeomStride ? a.geom[size_t(t) * kGeomStride + lane] : -1;
-    const int count = __shfl_sync(0xffffffffu, g, 19);
-    pidxLane = lane < 19 ? g : -1;
-    enablePred = count >= cfg.thr1 && __shfl_sync(0xffffffffu, g, 0) >= 0;
-  } else if (root && present && k == 0) {
-    S.nn[cidx] = 19;
-  }
-
   //-- encoder: normalise and transform the sums
   if (enc) {
     if (rsMul)
@@ -305,69 +385,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
 #pragma unroll
     for (int s = 0; s < 3; s++)
       buf = bfly_fwd(buf, bf[s], 1 << s, haar);
-  }
-
-  //-- prediction (intraDcPred)
-  int64_t pred = 0;
-  if (enablePred) {
-    int wsum = -1;
-    int64_t limLow = 0, limHigh = 0;
-    const int64_t fracMul = ext ? 1 : (int64_t(1) << kFracBits);
-    const int parentOnly = cfg.subnode ? 7 : 19;
-    for (int i = 0; i < 19; i++) {
-      const int q = __shfl_sync(0xffffffffu, pidxLane, i);
-      if (q < 0)
-        continue;
-      const int64_t v0 = P.rec[size_t(q) * A];
-      if (i) {
-        if (10 * v0 <= limLow || 10 * v0 >= limHigh)
-          continue;
-      } else {
-        limLow = 2 * v0;
-        limHigh = 25 * v0;
-      }
-      const int64_t mine = act ? P.rec[size_t(q) * A + k] : 0;
-      const int wp = cfg.predWeightParent[i];
-      const uint32_t mask = uint32_t(neigh_mask(i)) & occ;
-      uint32_t cmask = 0, nocc = 0;
-      int shift = 0, cfirst = 0;
-      if (i >= parentOnly && q < p) {
-        const int ii = i - 7;
-        const int sh = occu_shift(ii);
-        shift = ii < 9 ? sh : -sh;
-        nocc = P.occ[q];
-        cmask = (ii < 9 ? (nocc >> sh) : (nocc << sh)) & mask & 0xffu;
-        if (cmask)
-          cfirst = P.first[q];
-      }
-      if ((mask >> j) & 1) {
-        if ((cmask >> j) & 1) {
-          const int wc = cfg.predWeightChild[i - 7];
-          const int c = cfirst + __popc(nocc & ((1u << (j + shift)) - 1));
-          wsum += wc;
-          if (act)  // produced by an earlier block of this stage: poll the value
-            pred += poll_rec(&S.rec[size_t(c) * A + k]) * (wc * fracMul);
-        } else {
-          wsum += wp;
-          pred += mine * (wp * fracMul);
-        }
-      }
-    }
-    if (present && act) {
-      const int d = wsum + 1;
-      const int64_t div = (32768 + d / 2) / d;
-      int64_t v = fx_mul(pred, div);
-      if (haar)
-        v = (v >> kFracBits) << kFracBits;
-      else if (w0 > 1)
-        v = fx_mul(v, int64_t(isqrt64(uint64_t(w0) << (2 * kFracBits))));
-      pred = v;
-    } else {
-      pred = 0;
-    }
-#pragma unroll
-    for (int s = 0; s < 3; s++)
-      pred = bfly_fwd(pred, bf[s], 1 << s, haar);
   }
 
   //-- coefficients: lane (j, k) owns coefficient j of component k
@@ -378,181 +395,250 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     j == 0 ? 0x00u : j == 4 ? 0x01u : j == 2 ? 0x11u : j == 1 ? 0x15u
     : j == 6 ? 0x17u : j == 5 ? 0x57u : j == 3 ? 0x77u : 0x7fu;
   const int ncoef = __popc(existsMask);
+  const int myPos = __popc(existsMask & before);
 
-  LayerQp lq;
-  lq.luma = a.qt->layers[a.qpLayer][0];
-  lq.chromaOffset = a.qt->layers[a.qpLayer][1];
-  lq.maxQp = cfg.maxQp;
-  lq.fixedPointQpOffset = cfg.fixedPointQpOffset;
+  //-- prediction (intraDcPred)
+  int64_t pred = 0;
+  if (enablePred) {
+    int wsum = -1;
+    const int64_t fracMul = ext ? 1 : (int64_t(1) << kFracBits);
+    // parent-stage contributions; note which neighbours feed child values
+    uint32_t childNb = 0;
+    uint32_t vm = validMask;
+    while (vm) {
+      const int i = __ffs(vm) - 1;
+      vm &= vm - 1;
+      const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
+      int64_t mine = shfl_i64(nv0, i);
+      if (A > 1) {
+        const int64_t m1 = shfl_i64(nv1, i);
+        const int64_t m2 = shfl_i64(nv2, i);
+        mine = k == 0 ? mine : k == 1 ? m1 : m2;
+      }
+      const uint32_t mask = uint32_t(neigh_mask(i)) & occ;
+      uint32_t cmask = 0;
+      if (no) {  // only fetched for i >= parentOnly && q < p
+        const int ii = i - 7;
+        const int sh = occu_shift(ii);
+        cmask = (ii < 9 ? (no >> sh) : (no << sh)) & mask & 0xffu;
+      }
+      if (cmask)
+        childNb |= 1u << i;
+      if ((mask >> j) & 1) {
+        if ((cmask >> j) & 1) {
+          wsum += cfg.predWeightChild[i - 7];
+        } else {
+          const int wp = cfg.predWeightParent[i];
+          wsum += wp;
+          pred += mine * (wp * fracMul);
+        }
+      }
+    }
+    int64_t div = 0, sq = 0;
+    if (present && act) {
+      const int d = wsum + 1;
+      div = (32768 + d / 2) / d;
+      if (!haar && w0 > 1)
+        sq = int64_t(isqrt64(uint64_t(w0) << (2 * kFracBits)));
+    }
+    // child-stage contributions, produced by earlier blocks of this stage: the
+    // loads of up to four neighbours go out together, then whatever has not
+    // been produced yet is polled
+    uint32_t cm = childNb;
+    while (cm) {
+      int64_t v[4];
+      const int64_t* ad[4];
+      int wc[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        ad[u] = nullptr;
+        v[u] = 0;
+        wc[u] = 0;
+        if (cm) {
+          const int i = __ffs(cm) - 1;
+          cm &= cm - 1;
+          const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
+          const int cfirst = __shfl_sync(0xffffffffu, nfirst, i);
+          const int ii = i - 7;
+          const int sh = occu_shift(ii);
+          const int shift = ii < 9 ? sh : -sh;
+          const uint32_t cmask =
+            (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
+          if (act && ((cmask >> j) & 1)) {
+            const int c = cfirst + __popc(no & ((1u << (j + shift)) - 1));
+            ad[u] = &S.rec[size_t(c) * A + k];
+            v[u] = ld_rec(ad[u]);
+            wc[u] = cfg.predWeightChild[ii];
+          }
+        }
+      }
+      // wait for all of them at once
+      for (;;) {
+        bool pending = false;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          pending |= ad[u] && v[u] == kRecNotReady;
+        if (!pending)
+          break;
+        __nanosleep(a.pollNs);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (ad[u] && v[u] == kRecNotReady)
+            v[u] = ld_rec(ad[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        pred += v[u] * (wc[u] * fracMul);
+    }
+    if (present && act) {
+      int64_t v = fx_mul(pred, div);
+      if (haar)
+        v = (v >> kFracBits) << kFracBits;
+      else if (w0 > 1)
+        v = fx_mul(v, sq);
+      pred = v;
+    } else {
+      pred = 0;
+    }
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+      pred = bfly_fwd(pred, bf[s], 1 << s, haar);
+  }
 
   if (enc && enablePred && exists)
     buf -= pred;
 
+  // the coefficient of this lane before RDOQ (encoder)
+  int64_t qcMine = 0;
+  if (enc && exists && act)
+    qcMine = qz[k < 1 ? k : 1].quantize(fx_round(buf) << kAttrShift);
+
   bool flagMine = false;
-  const int myPos = __popc(existsMask & before);
-  const bool rdoq = enc && !haar;
   if (rdoq) {
-    int64_t d2 = 0, aq = 0, lam = 0;
-    int rc = 0;
-    if (exists) {
-      Quantizer q[2];
-      make_quantizers(lq, nodeQp0, nodeQp1, q);
-      if (act) {
-        const int64_t c = fx_round(buf);
-        d2 = c * c;
-        const int64_t qc = q[k < 1 ? k : 1].quantize(c << kAttrShift);
-        aq = qc < 0 ? -qc : qc;
-        rc = lut_log(aq);
-      }
-      const int64_t l0 = q[0].scale(1);
-      lam = l0 * l0 * (A == 1 ? 25 : 35);
+    int64_t d2 = 0;
+    int stat = 0;  // sum |q| (clamped to 3 per component) << 16 | sum of lut_log
+    if (exists && act) {
+      const int64_t c = fx_round(buf);
+      d2 = c * c;
+      const int64_t mag = qcMine < 0 ? -qcMine : qcMine;
+      stat = (mag > 3 ? 3 : int(mag)) << 16 | lut_log(mag);
     }
-    // sums over the components (lanes 8 and 16 away)
+    // sums over the components (lanes 8 and 16 away): every row ends up with them
     d2 += shfl_xor_i64(d2, 8);
     d2 += shfl_xor_i64(d2, 16);
-    aq += shfl_xor_i64(aq, 8);
-    aq += shfl_xor_i64(aq, 16);
-    rc += __shfl_xor_sync(0xffffffffu, rc, 8);
-    rc += __shfl_xor_sync(0xffffffffu, rc, 16);
-    // classification of this lane's coefficient: 0 = never resets the run
-    // (all components quantise to zero); kAlwaysRemoved = RDOQ removes it at
-    // any run length (never resets either); INT_MAX = always resets the run
-    // (sum of |q| >= 3, or RDOQ never fires); otherwise the run length from
-    // which RDOQ removes it
-    constexpr int kAlwaysRemoved = -2;
-    int thrMine = 0;
-    if (aq >= 3) {
-      thrMine = 0x7fffffff;
-    } else if (aq > 0) {
-      thrMine = rdoq_threshold(d2, lam, rc);
-      if (thrMine == 0)
-        thrMine = kAlwaysRemoved;
-    }
-
-    // the block's coefficients in scan order, replicated in every lane
-    int thr[8];
-#pragma unroll
-    for (int m = 0; m < 8; m++)
-      thr[m] = 0;
-    {
-      int n = 0;
-      const int kScan[8] = {0, 4, 2, 1, 6, 5, 3, 7};
-#pragma unroll
-      for (int si = 0; si < 8; si++) {
-        const int idx = kScan[si];
-        const int th = __shfl_sync(0xffffffffu, thrMine, idx);
-        const bool ex = (existsMask >> idx) & 1;  // uniform across the warp
-#pragma unroll
-        for (int m = 0; m < 8; m++)
-          if (ex && m == n)
-            thr[m] = th;
-        n += ex;
+    stat += __shfl_xor_sync(0xffffffffu, stat, 8);
+    stat += __shfl_xor_sync(0xffffffffu, stat, 16);
+    const int aq = stat >> 16, rc = stat & 0xffff;
+    int code = kCodeZero;
+    if (exists) {
+      if (aq >= 3) {
+        code = kCodeHard;
+      } else if (aq > 0) {
+        const int64_t l0 = qz[0].scale(1);
+        code = rdoq_code(d2, l0 * l0 * (A == 1 ? 25 : 35), rc);
       }
     }
-    bool hasS = false, hasH = false;
-    int lastH = -1;
-#pragma unroll
-    for (int m = 0; m < 8; m++)
-      if (m < ncoef) {
-        if (thr[m] == 0x7fffffff) {
-          hasH = true;
-          lastH = m;
-        } else if (thr[m] > 0) {
-          hasS = true;
-        }
-      }
+    flagMine = code == kCodeRemoved;
+    // the block's coefficients by scan position (the rows hold the same values)
+    const uint32_t softM =
+      __reduce_or_sync(0xffffffffu, exists && code >= 3 ? 1u << myPos : 0u);
+    const uint32_t hardM =
+      __reduce_or_sync(0xffffffffu, exists && code == kCodeHard ? 1u << myPos : 0u);
+    const bool hasS = softM != 0, hasH = hardM != 0;
+    unsigned long long codes = 0;
+    if (hasS) {
+      const uint32_t lo =
+        __reduce_or_sync(0xffffffffu, exists && myPos < 5 ? uint32_t(code) << (6 * myPos) : 0u);
+      const uint32_t hi = __reduce_or_sync(
+        0xffffffffu, exists && myPos >= 5 ? uint32_t(code) << (6 * (myPos - 5)) : 0u);
+      codes = lo | (unsigned long long)hi << 30;
+    }
 
     // publish what is known without looking at any other block
-    const TzRegion rg = a.regions[a.stageIdx];
     if (hasH) {
-      int tl = 0;
-#pragma unroll
-      for (int m = 0; m < 8; m++)
-        if (m > lastH && m < ncoef)
-          tl = tl >= thr[m] ? tl + 1 : 0;
+      // the run after the last coefficient that always resets it
+      const int lastH = 31 - __clz(hardM);
+      int e = 0, prev = lastH + 1;
+      uint32_t sm = softM & ~((2u << lastH) - 1);
+      while (sm) {
+        const int m = __ffs(sm) - 1;
+        sm &= sm - 1;
+        e += m - prev;
+        e = e >= thr_decode(int((codes >> (6 * m)) & 63)) ? e + 1 : 0;
+        prev = m + 1;
+      }
+      e += ncoef - prev;
       if (lane == 0)
-        st_release(&rg.words[t + 1], tz_pack(kTzExit, tl));
+        st_release(&a.words[t + 1], tz_pack(kTzExit, e));
     } else if (!hasS) {
       if (lane == 0)
-        st_release(&rg.words[t + 1], tz_pack(kTzTransparent, ncoef));
-    } else {
-      int mine = 0;
-#pragma unroll
-      for (int m = 0; m < 8; m++)
-        if (m == lane)
-          mine = thr[m] > 0 ? thr[m] : 0;
-      if (lane < 8)
-        rg.lists[size_t(t + 1) * 8 + lane] = mine;
-      __threadfence();
-      __syncwarp();
-      if (lane == 0)
-        st_release(&rg.words[t + 1], tz_pack(kTzClassified, ncoef));
+        st_release(&a.words[t + 1], tz_pack(kTzTransparent, ncoef));
+    } else if (lane == 0) {
+      a.lists[t + 1] = codes;
+      st_release(&a.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
 
-    // resolve this block's own decisions
-    bool linked = true;  // the run still reaches back beyond the block
-    int z = 0;           // its length inside the block while linked
-    int tl = 0;          // run length since the last reset inside the block
-#pragma unroll
-    for (int m = 0; m < 8; m++)
-      if (m < ncoef) {
-        bool f;
-        if (thr[m] <= 0)
-          f = thr[m] == kAlwaysRemoved;
-        else if (thr[m] == 0x7fffffff)
-          f = false;
-        else if (linked)
-          f = a.experiment == 1 ? false : tz_run_at_least(a, t, thr[m] - z);
+    // resolve this block's own decisions: only coefficients with a finite
+    // threshold need the run length (everything between them extends it)
+    if (hasS) {
+      bool linked = true;  // the run still reaches back beyond the block
+      int z = 0;           // its length inside the block while linked
+      int tl = 0;          // run length since the last reset inside the block
+      int prev = 0;
+      uint32_t ev = softM | hardM;
+      while (ev) {
+        const int m = __ffs(ev) - 1;
+        ev &= ev - 1;
+        if (linked)
+          z += m - prev;
         else
-          f = tl >= thr[m];
-        const bool keeps = thr[m] <= 0 || f;
+          tl += m - prev;
+        prev = m + 1;
+        bool f = false;
+        if ((softM >> m) & 1) {
+          const int th = thr_decode(int((codes >> (6 * m)) & 63));
+          if (linked)
+            f = a.experiment == 1 ? false : tz_run_at_least(a, t, th - z);
+          else
+            f = tl >= th;
+        }
         if (linked) {
-          if (keeps)
+          if (f)
             z++;
           else {
             linked = false;
             tl = 0;
           }
         } else {
-          tl = keeps ? tl + 1 : 0;
+          tl = f ? tl + 1 : 0;
         }
         if (m == myPos)
           flagMine = f;
       }
-    if (hasS && !hasH && lane == 0)
-      st_release(&rg.words[t + 1],
-                 linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
+      tl += ncoef - prev;
+      if (!hasH && lane == 0)
+        st_release(&a.words[t + 1],
+                   linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
+    }
   }
 
   //-- quantise / dequantise (RAHT.cpp:1672-1723)
-  {
-    int off0 = nodeQp0, off1 = nodeQp1;
-    if (j && a.acLayer < cfg.numAcLayers) {
-      off0 += a.qt->acQps[a.acLayer][j - 1][0];
-      off1 += a.qt->acQps[a.acLayer][j - 1][1];
+  if (exists && act) {
+    const Quantizer& qk = qz[k < 1 ? k : 1];
+    const int64_t pos = a.coefBase + c0 - (root ? 0 : p) + myPos;
+    int64_t qc;
+    if (enc) {
+      qc = flagMine ? 0 : qcMine;
+      a.coef[k * a.coefStride + pos] = int32_t(qc);
+    } else {
+      qc = a.coef[k * a.coefStride + pos];
     }
-    if (exists && act) {
-      Quantizer q[2];
-      make_quantizers(lq, off0, off1, q);
-      const Quantizer& qk = q[k < 1 ? k : 1];
-      const int64_t pos = a.coefBase + c0 - (root ? 0 : p) + myPos;
-      int64_t qc;
-      if (enc) {
-        const int64_t c = flagMine ? 0 : fx_round(buf);
-        qc = qk.quantize(c << kAttrShift);
-        a.coef[k * a.coefStride + pos] = int32_t(qc);
-      } else {
-        qc = a.coef[k * a.coefStride + pos];
-      }
-      pred += fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
-    }
+    pred += fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
   }
 
   //-- DC from the parent, inverse transform, store (RAHT.cpp:1726-1806)
-  if (!root && j == 0 && act) {
-    const int64_t v = P.recUs[size_t(p) * A + k];
-    pred = ext ? v : v * (int64_t(1) << (kFracBits - 2));
-  }
+  if (!root && j == 0 && act)
+    pred = ext ? dc : dc * (int64_t(1) << (kFracBits - 2));
 #pragma unroll
   for (int s = 2; s >= 0; s--)
     pred = bfly_inv(pred, bf[s], 1 << s, haar);
@@ -605,7 +691,7 @@ k_block_geom(const WarpBlockArgs a)
     S.nn[P.first[p] + __popc(occ & ((1u << lane) - 1))] = count;
 }
 
-__global__ void __launch_bounds__(kWarpBlockThreads)
+__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
   const int lane = threadIdx.x & 31;
