@@ -566,7 +566,7 @@ struct DeviceExec {
     int64_t cap = int64_t(numSMs) * perSM;
     static const int capShare = [] {  // percent of the machine all calls in flight may hold
       const char* e = getenv("PCCB200_BLOCK_SHARE");
-      return e ? atoi(e) : 50;
+      return e ? atoi(e) : 100;
     }();
     if (inFlight > 1)
       cap = cap * capShare / (100 * inFlight);
