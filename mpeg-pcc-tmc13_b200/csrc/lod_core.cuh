@@ -257,30 +257,73 @@ struct SubsampleDistanceFn {
 // Centroid subsampling (subsampleByOctree + ...WithCentroid, direction =
 // backward; PCCTMC3Common.h:2089-2194).  Groups of equal (code >> q) are
 // merged until a segment holds at least `period` entries; each segment
-// retains the entry nearest (L1) to the segment's centroid.  The greedy
-// segmentation is a sequential recurrence over group ends: one thread walks
-// it (the per-segment work is done in parallel afterwards).
-struct CentroidSegmentFn {
+// retains the entry nearest (L1) to the segment's centroid.
+//
+// The greedy segmentation is a recurrence over group ends (the next segment
+// starts where the previous one closed).  Parallel form: nxt[c] = first group
+// of the segment that follows a segment starting at group c (a binary search
+// per group: group sizes are prefix sums); the segment starts are the groups
+// reachable from group 0 through nxt, found by pointer doubling (jump tables
+// nxt^(2^i), then marking from the widest jump down).
+struct CentroidNextFn {
   const int32_t* cellFirst;  // group starts, nCells + 1
   int nCells;
-  int nInput;
   int period;
-  int32_t* segFirst;  // out: segment starts, terminated by nInput
-  int* nSeg;          // out
-  PCC_HD void operator()(int64_t) const
+  int32_t* nxt;  // out; nCells = no further segment
+  PCC_HD void operator()(int64_t ci) const
   {
-    int g0 = 0, s = 0;
-    for (int c = 0; c < nCells; c++) {
-      const int e = cellFirst[c + 1] - 1;  // last entry of group c
-      const int size = e - g0 + 1;
-      if (size < period && c != nCells - 1)
-        continue;
-      segFirst[s++] = g0;
-      g0 = e + 1;
+    const int c = int(ci);
+    const int g0 = cellFirst[c];
+    // the segment closes at the first group whose end makes it `period`
+    // long; the last group closes whatever is open
+    int lo = c, hi = nCells - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cellFirst[mid + 1] - g0 >= period)
+        hi = mid;
+      else
+        lo = mid + 1;
     }
-    segFirst[s] = nInput;
-    *nSeg = s;
+    nxt[c] = lo + 1;
   }
+};
+
+struct JumpSquareFn {  // dst = src o src
+  const int32_t* src;
+  int32_t* dst;
+  int nCells;
+  PCC_HD void operator()(int64_t c) const
+  {
+    const int j = src[c];
+    dst[c] = j < nCells ? src[j] : nCells;
+  }
+};
+
+// marks jump[c] for every marked c.  Threads of one pass may or may not see
+// marks set in the same pass: either way only groups on the path get marked,
+// and every mark of the earlier passes is seen, which is what completeness needs.
+struct JumpMarkFn {
+  const int32_t* jump;
+  uint8_t* mark;
+  int nCells;
+  PCC_HD void operator()(int64_t c) const
+  {
+    if (mark[c]) {
+      const int j = jump[c];
+      if (j < nCells)
+        mark[j] = 1;
+    }
+  }
+};
+
+struct MarkPred {
+  const uint8_t* mark;
+  PCC_HD bool operator()(int64_t c) const { return mark[c] != 0; }
+};
+struct SegmentEmit {
+  const int32_t* cellFirst;
+  int32_t* segFirst;
+  PCC_HD void operator()(int64_t rank, int64_t c) const { segFirst[rank] = cellFirst[c]; }
 };
 
 struct CentroidPickFn {

@@ -96,6 +96,12 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
   int32_t* cellFirst = ex.template alloc<int32_t>(size_t(N) + 1);
   int32_t* segFirst = ex.template alloc<int32_t>(size_t(N) + 1);
   int* decision = ex.template alloc<int>(N);
+  // centroid mode: jump tables of the segmentation, one per doubling level
+  int jumpLevels = 1;
+  while ((int64_t(1) << jumpLevels) < N)
+    jumpLevels++;
+  int32_t* jump =
+    cfg.decimation == 2 ? ex.template alloc<int32_t>(size_t(N) * jumpLevels) : nullptr;
   int* dCount = ex.template alloc<int>(4);
   unsigned long long* dStuck = ex.template alloc<unsigned long long>(1);
   uint32_t* p2p = ex.template alloc<uint32_t>(N);
@@ -143,10 +149,23 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
         fn.keep = keep;
         ex.subsample_distance(fn, nCells);
       } else {
-        ex.foreach(1, CentroidSegmentFn{cellFirst, nCells, nInput, cfg.samplingPeriod[lod],
-                                        segFirst, dCount + 1});
+        // segment starts = groups reachable from group 0 (see CentroidNextFn)
+        int levels = 1;
+        while ((int64_t(1) << levels) < nCells)
+          levels++;
+        ex.foreach(nCells, CentroidNextFn{cellFirst, nCells, cfg.samplingPeriod[lod], jump});
+        for (int i = 1; i < levels; i++)
+          ex.foreach(nCells, JumpSquareFn{jump + size_t(i - 1) * N, jump + size_t(i) * N, nCells});
+        uint8_t* mark = reinterpret_cast<uint8_t*>(decision);
+        ex.zero(mark, size_t(nCells));
+        const uint8_t one = 1;
+        ex.upload(mark, &one, 1);
+        for (int i = levels - 1; i >= 0; i--)
+          ex.foreach(nCells, JumpMarkFn{jump + size_t(i) * N, mark, nCells});
+        ex.compact(nCells, MarkPred{mark}, SegmentEmit{cellFirst, segFirst}, dCount + 1);
         int nSeg = 0;
         ex.download(&nSeg, dCount + 1, sizeof(int));
+        ex.upload(segFirst + nSeg, &n32, sizeof(int32_t));
         ex.foreach(nSeg, CentroidPickFn{v, input, segFirst, cfg.dist2 + lod, keep});
       }
       ex.compact(nInput, KeepPred{keep, 1}, ListEmit{input, retained}, dCount + 2);

@@ -76,6 +76,24 @@ shfl_i64(int64_t v, int src)
   return (int64_t)__shfl_sync(0xffffffffu, (long long)v, src);
 }
 
+// RahtKernel(wl, wr) out of line: the three butterfly levels share one copy of
+// the (long) square-root arithmetic, which keeps the kernel's hot code small
+// (instruction-cache misses showed up as a top stall reason on the big stages)
+struct RahtAB {
+  int64_t a, b;
+};
+#ifdef PCCB200_INLINE_AB
+__device__ __forceinline__ RahtAB
+#else
+__device__ __noinline__ RahtAB
+#endif
+raht_ab_shared(int wl, int wr)
+{
+  RahtAB r;
+  raht_ab(wl, wr, r.a, r.b);
+  return r;
+}
+
 // one butterfly stage; every lane calls it (the shuffle is unconditional)
 struct Bfly {
   int64_t a, b;
@@ -363,7 +381,9 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         bf[s].a = a.ab11a;
         bf[s].b = a.ab11b;
       } else {
-        raht_ab(wl, wr, bf[s].a, bf[s].b);
+        const RahtAB ab = raht_ab_shared(wl, wr);
+        bf[s].a = ab.a;
+        bf[s].b = ab.b;
       }
     }
     wcur = (lo || bf[s].both) ? wl + wr : 0;
