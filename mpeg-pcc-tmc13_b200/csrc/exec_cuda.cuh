@@ -446,6 +446,7 @@ struct DeviceExec {
     a.decision = fn.decision;
     a.keep = fn.keep;
     a.nb = alloc<int32_t>(size_t(nCells) * 19);
+    a.decPos = alloc<int4>(size_t(nCells));
     Scope sc(*this);
     const int64_t threads = int64_t(nCells) * 19;
     k_cell_neighbours<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(a);

@@ -4,10 +4,14 @@
 // host-testable definition):
 //   * k_cell_neighbours: one thread per (cell, neighbour offset) resolves the
 //     19 neighbour cells by binary search — geometry only, fully parallel;
-//   * k_subsample_cells: one warp per cell in Morton ticket order; 19 lanes
-//     poll the decision words of the earlier neighbour cells and fetch their
-//     retained points, then the cell's points are tested one after the other,
-//     all neighbours at once (ballot).
+//   * k_subsample_cells: one warp per cell in Morton ticket order.  A cell's
+//     latency is what bounds a level (cells wait for the decisions of earlier
+//     neighbour cells), so the cell's first points are fetched before the
+//     wait; then 19 lanes poll the decision words of the neighbour cells and
+//     read the retained point's position, which the deciding cell publishes
+//     next to its decision (one dependent access instead of three); the
+//     cell's points are tested one after the other, all neighbours at once
+//     (ballot).
 #pragma once
 
 #include "lod_core.cuh"
@@ -23,6 +27,7 @@ struct SubsampleCellsArgs {
   int* decision;
   uint8_t* keep;
   int32_t* nb;  // nCells * 19 neighbour cell indices (or -1)
+  int4* decPos;  // per cell: position of its retained point (valid once decision >= 0)
 };
 
 __global__ void __launch_bounds__(256)
@@ -64,42 +69,67 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
     if (t >= (unsigned long long)a.nCells)
       return;
     const int c = int(t);
+    const int q = lane < 19 ? a.nb[size_t(c) * 19 + lane] : -1;
+    const int i0 = a.cellFirst[c], i1 = a.cellFirst[c + 1];
+    // the first two points of the cell (the same in every lane), before the wait
+    int32_t pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};
+    {
+      const uint32_t ia = a.input[i0];
+      const uint32_t ib = i0 + 1 < i1 ? a.input[i0 + 1] : ia;
+      const int32_t* p = &a.v.pos[size_t(ia) * 3];
+      const int32_t* r = &a.v.pos[size_t(ib) * 3];
+      pa[0] = p[0];
+      pa[1] = p[1];
+      pa[2] = p[2];
+      pb[0] = r[0];
+      pb[1] = r[1];
+      pb[2] = r[2];
+    }
     // retained point of this lane's neighbour cell (if any)
     bool have = false;
     int32_t np[3] = {0, 0, 0};
-    if (lane < 19) {
-      const int q = a.nb[size_t(c) * 19 + lane];
-      if (q >= 0) {
-        int d;
-        while ((d = ld_acquire(&a.decision[q])) == kCellUndecided)
-          __nanosleep(32);
-        if (d >= 0) {
-          const int32_t* p = &a.v.pos[size_t(a.input[d]) * 3];
-          np[0] = p[0];
-          np[1] = p[1];
-          np[2] = p[2];
-          have = true;
-        }
+    if (q >= 0) {
+      int d;
+      while ((d = ld_acquire(&a.decision[q])) == kCellUndecided)
+        __nanosleep(32);
+      if (d >= 0) {
+        const int4 r = a.decPos[q];
+        np[0] = r.x;
+        np[1] = r.y;
+        np[2] = r.z;
+        have = true;
       }
     }
-    const int i0 = a.cellFirst[c], i1 = a.cellFirst[c + 1];
     int chosen = kCellNone;
     for (int i = i0; i < i1; i++) {
-      const int32_t* p = &a.v.pos[size_t(a.input[i]) * 3];
-      const int32_t pp[3] = {p[0], p[1], p[2]};
+      int32_t pp[3];
+      if (i == i0) {
+        pp[0] = pa[0], pp[1] = pa[1], pp[2] = pa[2];
+      } else if (i == i0 + 1) {
+        pp[0] = pb[0], pp[1] = pb[1], pp[2] = pb[2];
+      } else {
+        const int32_t* p = &a.v.pos[size_t(a.input[i]) * 3];
+        pp[0] = p[0], pp[1] = p[1], pp[2] = p[2];
+      }
       const bool hit = have && norm2_3(np, pp) <= radius2;
       const bool found = __ballot_sync(0xffffffffu, hit) != 0;
-      if (lane == 0)
-        a.keep[i] = found ? 0 : 1;
       if (!found) {
         chosen = i;
+        // the retained point's position travels with the decision
+        if (lane == 0) {
+          a.decPos[c] = make_int4(pp[0], pp[1], pp[2], 0);
+          st_release(&a.decision[c], chosen);
+          a.keep[i] = 1;
+        }
         for (int r = i + 1 + lane; r < i1; r += 32)
           a.keep[r] = 0;
         break;
       }
+      if (lane == 0)
+        a.keep[i] = 0;
     }
-    if (lane == 0)
-      st_release(&a.decision[c], chosen);
+    if (chosen == kCellNone && lane == 0)
+      st_release(&a.decision[c], kCellNone);
   }
 }
 
