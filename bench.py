@@ -34,9 +34,21 @@ import time
 # alias and a long dataflow kernel of one call blocks the short kernels of
 # another (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# keep stdout to the single JSON line (NCCL prints its version banner there)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries the single JSON line and nothing else: libraries that write to
+# file descriptor 1 (NCCL prints its version banner there) are sent to stderr
+# once main() has claimed it; emit_json() writes to the saved descriptor
+_JSON_FD = 1
+
+
+def claim_stdout():
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -247,7 +259,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 # ---------------------------------------------------------------------------
@@ -546,13 +558,14 @@ def run_ours(args):
                 "value": n / secs / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": kind,
                 "sample": f"1 frame of the same workload ({n} points, RGB + reflectance), "
                           f"{secs:.2f} s on one host core; host: {host_cpu_model()}"}
-        print(json.dumps(line))
+        emit_json(line)
     pool.shutdown()
     if distributed:
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
