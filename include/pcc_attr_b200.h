@@ -316,6 +316,33 @@ int pccb200_attr_lift_decode(const pccb200_lod_params* lod,
                              int32_t bitdepth, const int32_t* values_in,
                              const int8_t* lcp_coeffs);
 
+/* ---------------------------------------------------------------------------
+ * Spherical coordinates for attribute coding of LiDAR slices (the step before
+ * the attribute transforms when attr_aps.spherical_coord_flag is set). */
+
+/* convertXyzToRpl (tmc3/coordinate_conversion.cpp:44-69, with findLaser
+ * tmc3/geometry_octree.cpp:855-874 and iatan2 tmc3/misc.cpp:278-309).
+ * xyz: N x 3; laser_theta: num_theta elevation tangents (gps.angularTheta);
+ * rpl_out: N x 3 (radius, azimuth, laser index); bbox_out: min[3], max[3] of
+ * rpl_out (the Box3<int> the reference returns). */
+int pccb200_xyz_to_rpl(const int32_t laser_origin[3], const int32_t* laser_theta,
+                       int32_t num_theta, const int32_t* xyz, int64_t n,
+                       int32_t* rpl_out, int32_t bbox_out[6]);
+
+/* offsetAndScale (tmc3/coordinate_conversion.cpp:108-117), in place. */
+int pccb200_offset_and_scale(const int32_t min_pos[3], const int32_t axis_weight[3],
+                             int32_t* pos_inout, int64_t n);
+
+/* Both in one call, positions staying on the device in between: what the
+ * encoder and decoder do per slice (tmc3/encoder.cpp:1178-1196,
+ * tmc3/decoder.cpp:899-918).  min_pos == NULL: offset by the bounding-box
+ * minimum of the conversion (the intra case). */
+int pccb200_attr_spherical_positions(const int32_t laser_origin[3],
+                                     const int32_t* laser_theta, int32_t num_theta,
+                                     const int32_t axis_weight[3], const int32_t* min_pos,
+                                     const int32_t* xyz, int64_t n, int32_t* pos_out,
+                                     int32_t bbox_out[6]);
+
 #ifdef __cplusplus
 }
 #endif

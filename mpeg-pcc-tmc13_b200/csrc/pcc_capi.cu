@@ -23,6 +23,7 @@
 #include "morton_sort.cuh"
 #include "pcc_attr_b200.h"
 #include "raht_pipeline.cuh"
+#include "spherical.cuh"
 
 namespace pccb200 {
 
@@ -843,6 +844,67 @@ pccb200_attr_lift_decode(const pccb200_lod_params* lod, const pccb200_qpset* qps
   return attr_lift_common(false, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_out,
                           num_attrs, n, bitdepth, const_cast<int32_t*>(values_in),
                           const_cast<int8_t*>(lcp_coeffs));
+}
+
+//----------------------------------------------------------------------------
+// spherical coordinates (spherical.cuh)
+
+static int
+spherical_common(const int32_t* origin, const int32_t* theta, int32_t numTheta,
+                 const int32_t* weight, const int32_t* minPos, const int32_t* xyz, int64_t n,
+                 int32_t* out, int32_t* bbox)
+{
+  if (!origin || !theta || !xyz || !out || !bbox || numTheta < 1 || n < 0
+      || n > int64_t(INT32_MAX) / 3)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    const int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    const int32_t* dTheta = to_device(ex, theta, size_t(numTheta));
+    int32_t* dOut = ex.alloc<int32_t>(size_t(n) * 3);
+    run_xyz_to_rpl(ex, origin, dTheta, numTheta, dXyz, n, dOut, bbox, minPos, weight);
+    to_host(ex, out, dOut, size_t(n) * 3);
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_xyz_to_rpl(const int32_t laser_origin[3], const int32_t* laser_theta, int32_t num_theta,
+                   const int32_t* xyz, int64_t n, int32_t* rpl_out, int32_t bbox_out[6])
+{
+  return spherical_common(laser_origin, laser_theta, num_theta, nullptr, nullptr, xyz, n,
+                          rpl_out, bbox_out);
+}
+
+int
+pccb200_attr_spherical_positions(const int32_t laser_origin[3], const int32_t* laser_theta,
+                                 int32_t num_theta, const int32_t axis_weight[3],
+                                 const int32_t* min_pos, const int32_t* xyz, int64_t n,
+                                 int32_t* pos_out, int32_t bbox_out[6])
+{
+  if (!axis_weight)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return spherical_common(laser_origin, laser_theta, num_theta, axis_weight, min_pos, xyz, n,
+                          pos_out, bbox_out);
+}
+
+int
+pccb200_offset_and_scale(const int32_t min_pos[3], const int32_t axis_weight[3],
+                         int32_t* pos_inout, int64_t n)
+{
+  if (!min_pos || !axis_weight || !pos_inout || n < 0 || n > int64_t(INT32_MAX) / 3)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    int32_t* dPos = to_device(ex, pos_inout, size_t(n) * 3);
+    OffsetScaleFn os;
+    for (int k = 0; k < 3; k++) {
+      os.minPos[k] = min_pos[k];
+      os.weight[k] = axis_weight[k];
+    }
+    os.pos = dPos;
+    ex.foreach(n, os);
+    to_host(ex, pos_inout, dPos, size_t(n) * 3);
+    return PCCB200_OK;
+  });
 }
 
 }  // extern "C"

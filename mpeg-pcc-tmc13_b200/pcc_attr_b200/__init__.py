@@ -83,6 +83,7 @@ EXPORTS = [
     "pccb200_attr_lift_encode", "pccb200_attr_lift_decode", "pccb200_time_begin", "pccb200_time_end",
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
+    "pccb200_xyz_to_rpl", "pccb200_offset_and_scale", "pccb200_attr_spherical_positions",
 ]
 NUM_PHASES = 6
 PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
@@ -336,3 +337,41 @@ def attr_lift_decode(lod_params, qpset, xyz, values, lcp=None, bitdepth=8, qpoff
         _p(qpoffs, C.c_int32), _p(xyz, C.c_int32), _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n),
         C.c_int32(bitdepth), _p(values, C.c_int32), _p(l2, C.c_int8)))
     return attrs
+
+
+def _i3(v):
+    return (C.c_int32 * 3)(*[int(x) for x in v])
+
+
+def xyz_to_rpl(laser_origin, laser_theta, xyz):
+    """convertXyzToRpl -> (rpl [N,3], bbox (min[3], max[3]))"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    theta = np.ascontiguousarray(laser_theta, dtype=np.int32)
+    out = np.zeros_like(xyz)
+    bbox = np.zeros(6, dtype=np.int32)
+    _check(lib().pccb200_xyz_to_rpl(_i3(laser_origin), _p(theta, C.c_int32), C.c_int32(theta.size),
+                                    _p(xyz, C.c_int32), C.c_int64(xyz.shape[0]),
+                                    _p(out, C.c_int32), _p(bbox, C.c_int32)))
+    return out, (bbox[:3].copy(), bbox[3:].copy())
+
+
+def offset_and_scale(min_pos, axis_weight, pos):
+    """offsetAndScale -> new positions [N,3]"""
+    pos = np.ascontiguousarray(pos, dtype=np.int32).copy()
+    _check(lib().pccb200_offset_and_scale(_i3(min_pos), _i3(axis_weight), _p(pos, C.c_int32),
+                                          C.c_int64(pos.shape[0])))
+    return pos
+
+
+def attr_spherical_positions(laser_origin, laser_theta, axis_weight, xyz, min_pos=None):
+    """conversion + offsetAndScale in one call -> (positions [N,3], bbox of the conversion)"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    theta = np.ascontiguousarray(laser_theta, dtype=np.int32)
+    out = np.zeros_like(xyz)
+    bbox = np.zeros(6, dtype=np.int32)
+    _check(lib().pccb200_attr_spherical_positions(
+        _i3(laser_origin), _p(theta, C.c_int32), C.c_int32(theta.size), _i3(axis_weight),
+        None if min_pos is None else _i3(min_pos), _p(xyz, C.c_int32), C.c_int64(xyz.shape[0]),
+        _p(out, C.c_int32), _p(bbox, C.c_int32)))
+    return out, (bbox[:3].copy(), bbox[3:].copy())
+

@@ -4,6 +4,7 @@
 #include "exec_host.h"
 #include "lift_pipeline.cuh"
 #include "lod_pipeline.cuh"
+#include "spherical.cuh"
 #include "raht_pipeline.cuh"
 
 extern "C" int
@@ -57,3 +58,15 @@ emu_attr_lift(int forward, const pccb200_lod_params* lod, const pccb200_qpset* q
       lcp[l] = lcpLocal[l];
   return 0;
 }
+
+// spherical.cuh (host build): conversion + optional offsetAndScale
+extern "C" int
+emu_xyz_to_rpl(const int32_t* origin, const int32_t* theta, int numTheta, const int32_t* weight,
+               const int32_t* minPos, const int32_t* xyz, int64_t n, int32_t* out, int32_t* bbox)
+{
+  HostExec ex;
+  pccb200::run_xyz_to_rpl(ex, origin, theta, numTheta, xyz, n, out, bbox, minPos, weight);
+  return 0;
+}
+extern "C" int emu_iatan2(int y, int x) { return pccb200::iatan2_q20(y, x); }
+

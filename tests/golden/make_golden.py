@@ -116,7 +116,34 @@ def main():
             lod[f"{cname}/{i}/indexes"] = idx
             lod[f"{cname}/{i}/npl"] = npl
     np.savez_compressed(os.path.join(HERE, "lod_golden.npz"), **lod)
+    spherical_golden()
     print("golden vectors written")
+
+
+def spherical_golden():
+    """spherical-coordinate conversion (convertXyzToRpl + offsetAndScale of the
+    compiled reference, oracle/_ref/libtmc13_lift.so)"""
+    g = {}
+    xyz, _ = cloud_lidar(6000, seed=9)
+    rng = np.random.default_rng(17)
+    wide = rng.integers(-(1 << 20), 1 << 20, size=(3000, 3)).astype(np.int32)
+    wide[:200, :2] = rng.integers(-3, 4, size=(200, 2))  # around the axis, radius ~0
+    cases = [("lidar", xyz, (12, -7, 30), lidar_lasers(64)),
+             ("wide", wide, (0, 0, 0), lidar_lasers(16, -0.9, 0.9)),
+             ("one_laser", wide[:500], (5, 5, 5), lidar_lasers(1)),
+             ("two_lasers", wide[:500], (-9, 2, 0), lidar_lasers(2, -0.2, 0.3))]
+    g["names"] = np.array([c[0] for c in cases])
+    for name, pts, origin, theta in cases:
+        rpl, bbox = ref_xyz_to_rpl(origin, theta, pts)
+        w = ref_normalised_axes_weights(np.maximum(bbox[3:], 1))
+        g[f"{name}/xyz"] = pts
+        g[f"{name}/origin"] = np.array(origin, dtype=np.int32)
+        g[f"{name}/theta"] = theta
+        g[f"{name}/rpl"] = rpl
+        g[f"{name}/bbox"] = bbox
+        g[f"{name}/weight"] = np.array(w, dtype=np.int32)
+        g[f"{name}/scaled"] = ref_offset_and_scale(bbox[:3], w, rpl)
+    np.savez_compressed(os.path.join(HERE, "spherical_golden.npz"), **g)
 
 
 if __name__ == "__main__":

@@ -445,10 +445,7 @@ def ref_lift_encode(lod_params, qpset, lcp_enabled, xyz, attrs, bitdepth=8):
     """The reference's own lifting encoder (LoD build, weights, forward lifting,
     quantisation (+LCP), reconstruction): -> (values [N,A] predictor order,
     recon [N,A] input order, lcp coefficients)."""
-    global _liftref
-    if _liftref is None:
-        _liftref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtmc13_lift.so"))
-        _liftref.tmc13ref_lift_encode.restype = C.c_double
+    _load_liftref()
     xyz = np.ascontiguousarray(xyz, dtype=np.int32)
     attrs = np.ascontiguousarray(attrs, dtype=np.int32)
     n, a = attrs.shape
@@ -528,3 +525,73 @@ def emu_attr_lift(forward, lod_params, qpset, lcp_enabled, xyz, attrs, values=No
     lib.emu_attr_lift.restype = C.c_int
     return _attr_lift(lib.emu_attr_lift, forward, lod_params, qpset, lcp_enabled, xyz, attrs, values,
                       lcp, bitdepth)
+
+
+# --------------------------------------------------------------------------
+# spherical coordinates (row N2)
+
+def _load_liftref():
+    global _liftref
+    if _liftref is None:
+        _liftref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtmc13_lift.so"))
+        _liftref.tmc13ref_lift_encode.restype = C.c_double
+    return _liftref
+
+
+def _i3(v):
+    return (C.c_int32 * 3)(*[int(x) for x in v])
+
+
+def _run_rpl(fn, origin, theta, xyz, weight=None, min_pos=None, emu=False):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    theta = np.ascontiguousarray(theta, dtype=np.int32)
+    out = np.zeros_like(xyz)
+    bbox = np.zeros(6, dtype=np.int32)
+    if emu:
+        fn(_i3(origin), _ptr(theta, C.c_int32), C.c_int(theta.size),
+           None if weight is None else _i3(weight), None if min_pos is None else _i3(min_pos),
+           _ptr(xyz, C.c_int32), C.c_int64(xyz.shape[0]), _ptr(out, C.c_int32),
+           _ptr(bbox, C.c_int32))
+    else:
+        fn(_i3(origin), _ptr(theta, C.c_int32), C.c_int(theta.size), _ptr(xyz, C.c_int32),
+           C.c_int64(xyz.shape[0]), _ptr(out, C.c_int32), _ptr(bbox, C.c_int32))
+    return out, bbox
+
+
+def ref_xyz_to_rpl(origin, theta, xyz):
+    return _run_rpl(_load_liftref().tmc13ref_xyz_to_rpl, origin, theta, xyz)
+
+
+def oracle_xyz_to_rpl(origin, theta, xyz):
+    return _run_rpl(load_oracle().oracle_xyz_to_rpl, origin, theta, xyz)
+
+
+def emu_xyz_to_rpl(origin, theta, xyz, weight=None, min_pos=None):
+    return _run_rpl(load_emu().emu_xyz_to_rpl, origin, theta, xyz, weight, min_pos, emu=True)
+
+
+def _run_offset_scale(fn, min_pos, weight, pos):
+    pos = np.ascontiguousarray(pos, dtype=np.int32).copy()
+    fn(_i3(min_pos), _i3(weight), _ptr(pos, C.c_int32), C.c_int64(pos.shape[0]))
+    return pos
+
+
+def ref_offset_and_scale(min_pos, weight, pos):
+    return _run_offset_scale(_load_liftref().tmc13ref_offset_and_scale, min_pos, weight, pos)
+
+
+def oracle_offset_and_scale(min_pos, weight, pos):
+    return _run_offset_scale(load_oracle().oracle_offset_and_scale, min_pos, weight, pos)
+
+
+def ref_normalised_axes_weights(box_max, forced_max_log2=0):
+    out = (C.c_int32 * 3)()
+    _load_liftref().tmc13ref_normalised_axes_weights(_i3(box_max), C.c_int(forced_max_log2), out)
+    return [int(v) for v in out]
+
+
+def lidar_lasers(num=64, lo=-0.43, hi=0.04):
+    """elevation tangents of a spinning LiDAR in the reference's fixed point
+    (gps.angularTheta: tan(theta) * 2^18), ascending"""
+    return np.rint(np.tan(np.linspace(lo, hi, num)) * (1 << 18)).astype(np.int32)
+

@@ -338,3 +338,33 @@ def test_lifting_attribute_coder(b200, a):
                 assert np.array_equal(gl, ol)
             gd = b200.attr_lift_decode(_as_lod(b200, lp), q2, xyz, ov, lcp=ol if (a == 3 and lcp) else None)
             assert np.array_equal(gd, orr)
+
+
+def test_spherical_positions(b200):
+    """spherical-coordinate conversion for attribute coding (row N2): golden
+    vectors of the compiled reference, then a full-size LiDAR frame and an
+    adversarial random cloud against the oracle"""
+    pb = b200
+    g = np.load(os.path.join(GOLD, "spherical_golden.npz"))
+    for name in g["names"]:
+        origin, theta, xyz, w = (g[f"{name}/{k}"] for k in ("origin", "theta", "xyz", "weight"))
+        r, (mn, mx) = pb.xyz_to_rpl(origin, theta, xyz)
+        assert np.array_equal(r, g[f"{name}/rpl"])
+        assert np.array_equal(np.concatenate([mn, mx]), g[f"{name}/bbox"])
+        assert np.array_equal(pb.offset_and_scale(mn, w, r), g[f"{name}/scaled"])
+        s, (mn2, mx2) = pb.attr_spherical_positions(origin, theta, w, xyz)
+        assert np.array_equal(s, g[f"{name}/scaled"]) and np.array_equal(mn2, mn)
+        mp = (3, -2, 1)
+        s2, _ = pb.attr_spherical_positions(origin, theta, w, xyz, min_pos=mp)
+        assert np.array_equal(s2, oracle_offset_and_scale(mp, w, r))
+    rng = np.random.default_rng(3)
+    xyz, _ = cloud_lidar(1000000, seed=2)
+    wide = rng.integers(-(1 << 21), 1 << 21, size=(300000, 3)).astype(np.int32)
+    for pts, origin, theta in ((xyz, (40, -25, 310), lidar_lasers(64)),
+                               (wide, (0, 0, 0), lidar_lasers(48, -1.0, 1.0)),
+                               (wide[:1], (0, 0, 0), lidar_lasers(1))):
+        r, (mn, mx) = pb.xyz_to_rpl(origin, theta, pts)
+        o, ob = oracle_xyz_to_rpl(origin, theta, pts)
+        assert np.array_equal(r, o) and np.array_equal(np.concatenate([mn, mx]), ob)
+    with pytest.raises(pb.PccB200Error):
+        pb.xyz_to_rpl((0, 0, 0), np.zeros(0, dtype=np.int32), wide[:4])

@@ -121,3 +121,27 @@ def test_lifting_coder_empty_lods():
         ov, orr, ol = oracle_lift_encode(lp, qs, 1, x, a_)
         ev, er, el = emu_attr_lift(1, lp, qs, 1, x, a_)
         assert np.array_equal(ev, ov) and np.array_equal(er, orr) and np.array_equal(el, ol)
+
+
+def test_spherical_bodies():
+    """spherical.cuh (host build) against the oracle: conversion, bounding box,
+    offsetAndScale, and the fused call with either offset"""
+    emu, orc = load_emu(), load_oracle()
+    rng = np.random.default_rng(11)
+    for y, x in zip(rng.integers(-(1 << 30), 1 << 30, 3000), rng.integers(-(1 << 30), 1 << 30, 3000)):
+        assert emu.emu_iatan2(int(y), int(x)) == orc.oracle_iatan2(int(y), int(x))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spherical_golden.npz"))
+    for name in g["names"]:
+        origin, theta, xyz, w = (g[f"{name}/{k}"] for k in ("origin", "theta", "xyz", "weight"))
+        r, b = emu_xyz_to_rpl(origin, theta, xyz)
+        assert np.array_equal(r, g[f"{name}/rpl"]) and np.array_equal(b, g[f"{name}/bbox"])
+        s, b2 = emu_xyz_to_rpl(origin, theta, xyz, weight=w)  # offset = bounding-box minimum
+        assert np.array_equal(s, g[f"{name}/scaled"]) and np.array_equal(b2, b)
+        mp = (3, -2, 1)
+        s2, _ = emu_xyz_to_rpl(origin, theta, xyz, weight=w, min_pos=mp)
+        assert np.array_equal(s2, oracle_offset_and_scale(mp, w, r))
+    wide = rng.integers(-(1 << 21), 1 << 21, size=(20000, 3)).astype(np.int32)
+    theta = lidar_lasers(48, -1.0, 1.0)
+    r, b = emu_xyz_to_rpl((9, 9, 9), theta, wide)
+    o, ob = oracle_xyz_to_rpl((9, 9, 9), theta, wide)
+    assert np.array_equal(r, o) and np.array_equal(b, ob)

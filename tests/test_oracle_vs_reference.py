@@ -235,3 +235,49 @@ def test_live_lifting_encoder(a):
                     assert np.array_equal(rv, ov) and np.array_equal(rr, orr)
                     if a == 3 and lcp:
                         assert np.array_equal(rl, ol)
+
+
+# --------------------------------------------------------------------------
+# spherical coordinates for attribute coding (row N2)
+
+def test_spherical_golden():
+    """oracle against the committed outputs of the compiled reference"""
+    g = np.load(os.path.join(GOLD, "spherical_golden.npz"))
+    for name in g["names"]:
+        rpl, bbox = oracle_xyz_to_rpl(g[f"{name}/origin"], g[f"{name}/theta"], g[f"{name}/xyz"])
+        assert np.array_equal(rpl, g[f"{name}/rpl"]) and np.array_equal(bbox, g[f"{name}/bbox"])
+        sc = oracle_offset_and_scale(bbox[:3], g[f"{name}/weight"], rpl)
+        assert np.array_equal(sc, g[f"{name}/scaled"])
+
+
+@needs_liftref
+def test_live_spherical():
+    lib, orc = _load_liftref_for_test(), load_oracle()
+    rng = np.random.default_rng(5)
+    # the fixed-point arc tangent, all quadrants, axes, tiny and large arguments
+    ys = np.concatenate([rng.integers(-(1 << 30), 1 << 30, 4000), rng.integers(-300, 300, 2000),
+                         [0, 0, 1, -1, 5, -5, 0, (1 << 30), -(1 << 30)]])
+    xs = np.concatenate([rng.integers(-(1 << 30), 1 << 30, 4000), rng.integers(-300, 300, 2000),
+                         [0, 7, 0, 0, 5, 5, -9, (1 << 30), (1 << 30)]])
+    for y, x in zip(ys, xs):
+        assert orc.oracle_iatan2(int(y), int(x)) == lib.tmc13ref_iatan2(int(y), int(x)), (y, x)
+    # whole conversion on LiDAR-shaped and uniformly random clouds
+    xyz, _ = cloud_lidar(30000, seed=4)
+    wide = rng.integers(-(1 << 21), 1 << 21, size=(20000, 3)).astype(np.int32)
+    for pts, origin, theta in ((xyz, (3, -4, 20), lidar_lasers(64)),
+                               (xyz, (0, 0, 0), lidar_lasers(32, -0.3, 0.1)),
+                               (wide, (100, -100, 7), lidar_lasers(40, -1.2, 1.2)),
+                               (wide[:100], (0, 0, 0), lidar_lasers(1)),
+                               (wide[:100], (0, 0, 0), lidar_lasers(2)),
+                               (wide[:1], (1, 2, 3), lidar_lasers(5))):
+        r, rb = ref_xyz_to_rpl(origin, theta, pts)
+        o, ob = oracle_xyz_to_rpl(origin, theta, pts)
+        assert np.array_equal(r, o) and np.array_equal(rb, ob)
+        w = ref_normalised_axes_weights(np.maximum(rb[3:], 1))
+        for mp in (rb[:3], (0, 0, 0), (-50, 7, 1)):
+            assert np.array_equal(ref_offset_and_scale(mp, w, r), oracle_offset_and_scale(mp, w, o))
+
+
+def _load_liftref_for_test():
+    from pcc_testlib import _load_liftref
+    return _load_liftref()
