@@ -368,3 +368,35 @@ def test_spherical_positions(b200):
         assert np.array_equal(r, o) and np.array_equal(np.concatenate([mn, mx]), ob)
     with pytest.raises(pb.PccB200Error):
         pb.xyz_to_rpl((0, 0, 0), np.zeros(0, dtype=np.int32), wide[:4])
+
+
+def test_repeatability(b200):
+    """the dataflow kernels are timing dependent inside (tickets, polls): the
+    same call must give the same bits every time, also with a tiny persistent
+    grid (looping warps) — run as a subprocess so the environment knob applies"""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import pcc_attr_b200 as pb\n"
+        "from pcc_testlib import cloud_lidar, make_params, make_qpset\n"
+        "xyz, attrs = cloud_lidar(120000, seed=6, a=3)\n"
+        "p = pb.RahtParams.from_buffer_copy(bytes(make_params())); q = pb.QpSet.from_buffer_copy(bytes(make_qpset(qp=34)))\n"
+        "ref = None\n"
+        "for i in range(25):\n"
+        "    rec, coef = pb.attr_raht_encode(p, q, xyz, attrs)\n"
+        "    if ref is None: ref = (rec.copy(), coef.copy())\n"
+        "    assert np.array_equal(rec, ref[0]) and np.array_equal(coef, ref[1]), i\n"
+        "print('same', int(np.abs(coef).sum()))\n"
+    ) % (os.path.join(ROOT, "mpeg-pcc-tmc13_b200"), os.path.join(ROOT, "tests"))
+    outs = []
+    for grid in ("", "8"):
+        env = dict(os.environ)
+        if grid:
+            env["PCCB200_BLOCK_GRID"] = grid
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and outs[0].startswith("same")
