@@ -343,6 +343,37 @@ int pccb200_attr_spherical_positions(const int32_t laser_origin[3],
                                      const int32_t* xyz, int64_t n, int32_t* pos_out,
                                      int32_t bbox_out[6]);
 
+/* ---------------------------------------------------------------------------
+ * Symbol preparation for the entropy coder: the walk over the coefficients
+ * right after the forward transform (tmc3/AttributeEncoder.cpp:1279-1291 one
+ * component, :1346-1362 three).  For every position with a non-zero
+ * coefficient, in coding order:
+ *   zero_runs_out[s]       all-zero positions since the previous symbol (the
+ *                          argument of PCCResidualsEncoder::encodeRunLength)
+ *   values_out[s*A + k]    the coefficients (arguments of encode())
+ *   ctx_out[s]             A == 3, may be NULL: b0 | b1<<1 | b2<<2 | b3<<3, the
+ *                          context selectors encode() derives from |v1|, |v2|
+ *                          (tmc3/AttributeEncoder.cpp:271-296)
+ * *count_out symbols; *tail_run_out = all-zero positions after the last one
+ * (a final encodeRunLength if non-zero).  Output buffers hold n symbols.
+ * coeffs: A x n planar, as written by pccb200_raht_forward. */
+int pccb200_coeff_symbols(const int32_t* coeffs, int32_t num_attrs, int32_t n,
+                          int32_t* zero_runs_out, int32_t* values_out,
+                          uint8_t* ctx_out, int32_t* count_out,
+                          int32_t* tail_run_out);
+
+/* pccb200_attr_raht_encode followed by pccb200_coeff_symbols with the
+ * coefficients never leaving the device: what crosses PCIe is the symbol
+ * stream (usually a small fraction of N x A) and the reconstruction. */
+int pccb200_attr_raht_encode_symbols(const pccb200_raht_params* params,
+                                     const pccb200_qpset* qpset,
+                                     const int32_t* point_qp_offsets,
+                                     const int32_t* xyz, int32_t* attrs_inout,
+                                     int32_t num_attrs, int32_t n, int32_t bitdepth,
+                                     int32_t* zero_runs_out, int32_t* values_out,
+                                     uint8_t* ctx_out, int32_t* count_out,
+                                     int32_t* tail_run_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@
 #include "pcc_attr_b200.h"
 #include "raht_pipeline.cuh"
 #include "spherical.cuh"
+#include "symbols.cuh"
 
 namespace pccb200 {
 
@@ -903,6 +904,79 @@ pccb200_offset_and_scale(const int32_t min_pos[3], const int32_t axis_weight[3],
     os.pos = dPos;
     ex.foreach(n, os);
     to_host(ex, pos_inout, dPos, size_t(n) * 3);
+    return PCCB200_OK;
+  });
+}
+
+//----------------------------------------------------------------------------
+// symbol preparation for the entropy coder (symbols.cuh)
+
+static void
+symbols_to_host(DeviceExec& ex, const int32_t* dRuns, const int32_t* dValues, const uint8_t* dCtx,
+                int count, int A, int32_t* runs, int32_t* values, uint8_t* ctx)
+{
+  to_host(ex, runs, dRuns, size_t(count));
+  to_host(ex, values, dValues, size_t(count) * A);
+  if (ctx && A == 3)
+    to_host(ex, ctx, dCtx, size_t(count));
+}
+
+int
+pccb200_coeff_symbols(const int32_t* coeffs, int32_t num_attrs, int32_t n,
+                      int32_t* zero_runs_out, int32_t* values_out, uint8_t* ctx_out,
+                      int32_t* count_out, int32_t* tail_run_out)
+{
+  if (!coeffs || !zero_runs_out || !values_out || !count_out || !tail_run_out || n <= 0
+      || (num_attrs != 1 && num_attrs != 3))
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    const int A = num_attrs;
+    const int32_t* dCoef = to_device(ex, coeffs, size_t(n) * A);
+    int32_t* dRuns = ex.alloc<int32_t>(size_t(n));
+    int32_t* dValues = ex.alloc<int32_t>(size_t(n) * A);
+    uint8_t* dCtx = ex.alloc<uint8_t>(size_t(n));
+    int count = 0, tail = 0;
+    run_coeff_symbols(ex, dCoef, n, A, n, dRuns, dValues, dCtx, &count, &tail);
+    symbols_to_host(ex, dRuns, dValues, dCtx, count, A, zero_runs_out, values_out, ctx_out);
+    *count_out = count;
+    *tail_run_out = tail;
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_attr_raht_encode_symbols(const pccb200_raht_params* params, const pccb200_qpset* qpset,
+                                 const int32_t* point_qp_offsets, const int32_t* xyz,
+                                 int32_t* attrs_inout, int32_t num_attrs, int32_t n,
+                                 int32_t bitdepth, int32_t* zero_runs_out, int32_t* values_out,
+                                 uint8_t* ctx_out, int32_t* count_out, int32_t* tail_run_out)
+{
+  const int64_t offs[2] = {0, n};
+  int rc = check_slices(params, qpset, xyz, attrs_inout, values_out, num_attrs, bitdepth, offs, 1);
+  if (rc != PCCB200_OK)
+    return rc;
+  if (!zero_runs_out || !count_out || !tail_run_out || num_attrs == 2)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    const int A = num_attrs;
+    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    int32_t* dAttrsIn = to_device(ex, attrs_inout, size_t(n) * A);
+    int32_t* dQpoIn = point_qp_offsets ? to_device(ex, point_qp_offsets, size_t(n) * 2) : nullptr;
+    int32_t* dCoef = ex.alloc<int32_t>(size_t(n) * A);
+    int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+    int rc2 = attr_raht_slice(ex, true, params, qpset, dQpoIn, dXyz, dAttrsIn, dOut, A, bitdepth,
+                              n, dCoef, n);
+    if (rc2 != PCCB200_OK)
+      return rc2;
+    to_host(ex, attrs_inout, dOut, size_t(n) * A);
+    int32_t* dRuns = ex.alloc<int32_t>(size_t(n));
+    int32_t* dValues = ex.alloc<int32_t>(size_t(n) * A);
+    uint8_t* dCtx = ex.alloc<uint8_t>(size_t(n));
+    int count = 0, tail = 0;
+    run_coeff_symbols(ex, dCoef, n, A, n, dRuns, dValues, dCtx, &count, &tail);
+    symbols_to_host(ex, dRuns, dValues, dCtx, count, A, zero_runs_out, values_out, ctx_out);
+    *count_out = count;
+    *tail_run_out = tail;
     return PCCB200_OK;
   });
 }

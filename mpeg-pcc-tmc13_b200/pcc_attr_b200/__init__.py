@@ -84,6 +84,7 @@ EXPORTS = [
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
     "pccb200_xyz_to_rpl", "pccb200_offset_and_scale", "pccb200_attr_spherical_positions",
+    "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols",
 ]
 NUM_PHASES = 6
 PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
@@ -374,4 +375,40 @@ def attr_spherical_positions(laser_origin, laser_theta, axis_weight, xyz, min_po
         None if min_pos is None else _i3(min_pos), _p(xyz, C.c_int32), C.c_int64(xyz.shape[0]),
         _p(out, C.c_int32), _p(bbox, C.c_int32)))
     return out, (bbox[:3].copy(), bbox[3:].copy())
+
+
+def coeff_symbols(coeffs):
+    """planar coefficients [A, N] -> (zero_runs[S], values[S, A], ctx[S] or None, tail_run)"""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int32)
+    a, n = coeffs.shape
+    runs = np.zeros(n, dtype=np.int32)
+    values = np.zeros((n, a), dtype=np.int32)
+    ctx = np.zeros(n, dtype=np.uint8)
+    cnt, tail = C.c_int32(0), C.c_int32(0)
+    _check(lib().pccb200_coeff_symbols(_p(coeffs, C.c_int32), C.c_int32(a), C.c_int32(n),
+                                       _p(runs, C.c_int32), _p(values, C.c_int32),
+                                       _p(ctx, C.c_uint8), C.byref(cnt), C.byref(tail)))
+    s = cnt.value
+    return runs[:s].copy(), values[:s].copy(), (ctx[:s].copy() if a == 3 else None), tail.value
+
+
+def attr_raht_encode_symbols(params, qpset, xyz, attrs, bitdepth=8, qpoffs=None):
+    """-> (reconstruction [N, A], zero_runs, values, ctx, tail_run): the attribute
+    encoder call handing over the entropy coder's symbol stream"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+    n, a = attrs.shape
+    runs = np.zeros(n, dtype=np.int32)
+    values = np.zeros((n, a), dtype=np.int32)
+    ctx = np.zeros(n, dtype=np.uint8)
+    cnt, tail = C.c_int32(0), C.c_int32(0)
+    if qpoffs is not None:
+        qpoffs = np.ascontiguousarray(qpoffs, dtype=np.int32)
+    _check(lib().pccb200_attr_raht_encode_symbols(
+        C.byref(params), C.byref(qpset), _p(qpoffs, C.c_int32), _p(xyz, C.c_int32),
+        _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n), C.c_int32(bitdepth),
+        _p(runs, C.c_int32), _p(values, C.c_int32), _p(ctx, C.c_uint8), C.byref(cnt),
+        C.byref(tail)))
+    s = cnt.value
+    return attrs, runs[:s].copy(), values[:s].copy(), (ctx[:s].copy() if a == 3 else None), tail.value
 

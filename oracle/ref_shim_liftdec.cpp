@@ -84,3 +84,45 @@ tmc13ref_lift_decode_values(
   decoder.stop();
   return 0;
 }
+
+// The symbol stream as the reference's RAHT decoder reads it
+// (tmc3/AttributeDecoder.cpp:553-565 one component, :641-654 three): every
+// decodeRunLength() result and every decoded value, in order.
+extern "C" int
+tmc13ref_decode_symbol_stream(
+  const uint8_t* buf, int len, int n, int numAttrs, int32_t* runsOut, int32_t* valuesOut,
+  int32_t* tailRunOut)
+{
+  AttributeBrickHeader abh{};
+  SequenceParameterSet sps{};
+  AttributeContexts ctxtMem;
+  ctxtMem.reset();
+  PCCResidualsDecoder decoder(abh, ctxtMem);
+  decoder.start(sps, reinterpret_cast<const char*>(buf), len);
+  int count = 0;
+  int zeroRunRem = 0;
+  int lastRun = 0;
+  bool pendingRun = false;
+  for (int i = 0; i < n; i++) {
+    if (--zeroRunRem < 0) {
+      zeroRunRem = decoder.decodeRunLength();
+      lastRun = zeroRunRem;
+      pendingRun = true;
+    }
+    if (!zeroRunRem) {
+      int32_t values[3] = {};
+      if (numAttrs == 3)
+        decoder.decode(values);
+      else
+        values[0] = decoder.decode();
+      runsOut[count] = lastRun;
+      for (int k = 0; k < numAttrs; k++)
+        valuesOut[count * numAttrs + k] = values[k];
+      count++;
+      pendingRun = false;
+    }
+  }
+  *tailRunOut = pendingRun ? lastRun : 0;
+  decoder.stop();
+  return count;
+}

@@ -5,6 +5,7 @@
 #include "lift_pipeline.cuh"
 #include "lod_pipeline.cuh"
 #include "spherical.cuh"
+#include "symbols.cuh"
 #include "raht_pipeline.cuh"
 
 extern "C" int
@@ -69,4 +70,16 @@ emu_xyz_to_rpl(const int32_t* origin, const int32_t* theta, int numTheta, const 
   return 0;
 }
 extern "C" int emu_iatan2(int y, int x) { return pccb200::iatan2_q20(y, x); }
+
+// symbols.cuh (host build)
+extern "C" int
+emu_coeff_symbols(const int32_t* coeffs, int A, int n, int32_t* runs, int32_t* values, uint8_t* ctx,
+                  int32_t* tail)
+{
+  HostExec ex;
+  int count = 0, t = 0;
+  pccb200::run_coeff_symbols(ex, coeffs, n, A, n, runs, values, ctx, &count, &t);
+  *tail = t;
+  return count;
+}
 

@@ -117,7 +117,33 @@ def main():
             lod[f"{cname}/{i}/npl"] = npl
     np.savez_compressed(os.path.join(HERE, "lod_golden.npz"), **lod)
     spherical_golden()
+    symbols_golden()
     print("golden vectors written")
+
+
+SYMBOL_GOLDEN_CASES = [("shell3", 3, 16), ("shell1", 1, 22), ("lidar3", 3, 28), ("lidar1", 1, 10)]
+
+
+def symbols_golden():
+    """the symbol stream the reference's RAHT attribute decoder reads from the
+    payload of the reference's own encoder (oracle/_ref/libtmc13_lift.so)"""
+    g = {}
+    for name, a, qp in SYMBOL_GOLDEN_CASES:
+        if name.startswith("shell"):
+            xyz, attrs = cloud_shell(5000, bits=7, seed=5, a=a)
+        else:
+            xyz, attrs = cloud_lidar(5000, seed=5, a=a)
+        params, qs = make_params(), make_qpset(qp=qp)
+        payload, recon = ref_raht_encode_payload(params, qs, xyz, attrs)
+        runs, vals, tail = ref_decode_symbol_stream(payload, len(xyz), a)
+        g[f"{name}/xyz"] = xyz
+        g[f"{name}/attrs"] = attrs
+        g[f"{name}/runs"] = runs
+        g[f"{name}/values"] = vals
+        g[f"{name}/tail"] = np.int32(tail)
+        g[f"{name}/recon"] = recon
+        g[f"{name}/payload"] = np.frombuffer(payload, dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "symbols_golden.npz"), **g)
 
 
 def spherical_golden():

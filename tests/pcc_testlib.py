@@ -595,3 +595,77 @@ def lidar_lasers(num=64, lo=-0.43, hi=0.04):
     (gps.angularTheta: tan(theta) * 2^18), ascending"""
     return np.rint(np.tan(np.linspace(lo, hi, num)) * (1 << 18)).astype(np.int32)
 
+
+# --------------------------------------------------------------------------
+# symbol preparation for the entropy coder (row N1)
+
+def _run_symbols(fn, coeffs):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.int32)
+    a, n = coeffs.shape
+    runs = np.zeros(n, dtype=np.int32)
+    values = np.zeros((n, a), dtype=np.int32)
+    ctx = np.zeros(n, dtype=np.uint8)
+    tail = C.c_int32(0)
+    fn.restype = C.c_int
+    cnt = fn(_ptr(coeffs, C.c_int32), C.c_int(a), C.c_int(n), _ptr(runs, C.c_int32),
+             _ptr(values, C.c_int32), _ptr(ctx, C.c_uint8), C.byref(tail))
+    return runs[:cnt].copy(), values[:cnt].copy(), (ctx[:cnt].copy() if a == 3 else None), tail.value
+
+
+def oracle_coeff_symbols(coeffs):
+    return _run_symbols(load_oracle().oracle_coeff_symbols, coeffs)
+
+
+def emu_coeff_symbols(coeffs):
+    return _run_symbols(load_emu().emu_coeff_symbols, coeffs)
+
+
+def ref_raht_encode_payload(params, qpset, xyz, attrs, bitdepth=8):
+    """the reference's own RAHT attribute encoder (sort, transform, coefficient
+    walk, arithmetic coding) -> (payload bytes, reconstruction [N, A])"""
+    lib = _load_liftref()
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    attrs = np.ascontiguousarray(attrs, dtype=np.int32)
+    n, a = attrs.shape
+    cap = 64 + n * a * 8
+    buf = np.zeros(cap, dtype=np.uint8)
+    recon = np.zeros((n, a), dtype=np.int32)
+    lib.tmc13ref_raht_encode_payload.restype = C.c_int
+    ln = lib.tmc13ref_raht_encode_payload(
+        C.byref(params), C.byref(qpset), _ptr(xyz, C.c_int32), _ptr(attrs, C.c_int32), C.c_int(n),
+        C.c_int(a), C.c_int(bitdepth), _ptr(buf, C.c_uint8), C.c_int(cap), _ptr(recon, C.c_int32))
+    assert ln >= 0
+    return bytes(buf[:ln]), recon
+
+
+def ref_symbols_payload(mode, runs, values, ctx, tail, n):
+    """a symbol stream through the reference's PCCResidualsEncoder -> payload bytes
+    (mode 0: its encode() members; mode 1: encodeSymbol with the given selectors)"""
+    lib = _load_liftref()
+    runs = np.ascontiguousarray(runs, dtype=np.int32)
+    values = np.ascontiguousarray(values, dtype=np.int32)
+    a = values.shape[1]
+    c8 = np.ascontiguousarray(ctx if ctx is not None else np.zeros(len(runs)), dtype=np.uint8)
+    cap = 64 + n * a * 8
+    buf = np.zeros(cap, dtype=np.uint8)
+    lib.tmc13ref_symbols_payload.restype = C.c_int
+    ln = lib.tmc13ref_symbols_payload(
+        C.c_int(mode), _ptr(runs, C.c_int32), _ptr(values, C.c_int32), _ptr(c8, C.c_uint8),
+        C.c_int(len(runs)), C.c_int(tail), C.c_int(a), C.c_int(n), _ptr(buf, C.c_uint8), C.c_int(cap))
+    assert ln >= 0
+    return bytes(buf[:ln])
+
+
+def ref_decode_symbol_stream(payload, n, a):
+    """the symbol stream as the reference's RAHT decoder reads it"""
+    lib = _load_liftref()
+    buf = np.frombuffer(payload, dtype=np.uint8).copy()
+    runs = np.zeros(n, dtype=np.int32)
+    values = np.zeros((n, a), dtype=np.int32)
+    tail = C.c_int32(0)
+    lib.tmc13ref_decode_symbol_stream.restype = C.c_int
+    cnt = lib.tmc13ref_decode_symbol_stream(
+        _ptr(buf, C.c_uint8), C.c_int(len(buf)), C.c_int(n), C.c_int(a), _ptr(runs, C.c_int32),
+        _ptr(values, C.c_int32), C.byref(tail))
+    return runs[:cnt].copy(), values[:cnt].copy(), tail.value
+

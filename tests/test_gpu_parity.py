@@ -400,3 +400,35 @@ def test_repeatability(b200):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1] and outs[0].startswith("same")
+
+
+def test_entropy_coder_symbols(b200):
+    """symbol preparation for the entropy coder (row N1): the stream the fused
+    encoder call hands over equals the one decoded from the reference
+    encoder's payload (golden), and the oracle's on larger clouds"""
+    from golden.make_golden import SYMBOL_GOLDEN_CASES
+
+    pb = b200
+    g = np.load(os.path.join(GOLD, "symbols_golden.npz"))
+    for name, a, qp in SYMBOL_GOLDEN_CASES:
+        p, q = _as(pb, make_params(), make_qpset(qp=qp))
+        rec, runs, vals, ctx, tail = pb.attr_raht_encode_symbols(p, q, g[f"{name}/xyz"], g[f"{name}/attrs"])
+        assert np.array_equal(runs, g[f"{name}/runs"]) and np.array_equal(vals, g[f"{name}/values"])
+        assert tail == int(g[f"{name}/tail"]) and np.array_equal(rec, g[f"{name}/recon"])
+    rng = np.random.default_rng(8)
+    for a in (1, 3):
+        xyz, attrs = cloud_lidar(300000, seed=3, a=a)
+        params, qs = make_params(), make_qpset(qp=34)
+        p, q = _as(pb, params, qs)
+        rec, coef = pb.attr_raht_encode(p, q, xyz, attrs)
+        o = oracle_coeff_symbols(coef)
+        s = pb.coeff_symbols(coef)
+        rec2, runs, vals, ctx, tail = pb.attr_raht_encode_symbols(p, q, xyz, attrs)
+        for got in (s, (runs, vals, ctx, tail)):
+            assert np.array_equal(got[0], o[0]) and np.array_equal(got[1], o[1]) and got[3] == o[3]
+            assert (o[2] is None and got[2] is None) or np.array_equal(got[2], o[2])
+        assert np.array_equal(rec2, rec)
+        for n, density in ((1, 0.0), (1, 1.0), (100000, 0.0), (100000, 0.7)):
+            c = (rng.integers(-9, 10, size=(a, n)) * (rng.random((a, n)) < density)).astype(np.int32)
+            o, s = oracle_coeff_symbols(c), pb.coeff_symbols(c)
+            assert np.array_equal(s[0], o[0]) and np.array_equal(s[1], o[1]) and s[3] == o[3]

@@ -145,3 +145,25 @@ def test_spherical_bodies():
     r, b = emu_xyz_to_rpl((9, 9, 9), theta, wide)
     o, ob = oracle_xyz_to_rpl((9, 9, 9), theta, wide)
     assert np.array_equal(r, o) and np.array_equal(b, ob)
+
+
+def test_symbol_bodies():
+    """symbols.cuh (host build) against the oracle: synthetic coefficient
+    planes with every run-length pattern, and real transform output"""
+    rng = np.random.default_rng(2)
+    for a in (1, 3):
+        for n, density in ((1, 1.0), (1, 0.0), (7, 0.5), (5000, 0.02), (5000, 0.9), (4096, 0.0)):
+            coef = (rng.integers(-40, 41, size=(a, n)) * (rng.random((a, n)) < density)).astype(np.int32)
+            o, e = oracle_coeff_symbols(coef), emu_coeff_symbols(coef)
+            assert np.array_equal(o[0], e[0]) and np.array_equal(o[1], e[1]) and o[3] == e[3]
+            assert (o[2] is None and e[2] is None) or np.array_equal(o[2], e[2])
+            # the stream expands back to the planes
+            back = np.zeros_like(coef)
+            pos = np.cumsum(o[0] + 1) - 1
+            back[:, pos] = o[1].T
+            assert np.array_equal(back, coef) and (len(pos) == 0 or pos[-1] + o[3] == n - 1)
+        xyz, attrs = cloud_shell(12000, bits=8, seed=4, a=a)
+        mort, a_s, order = sort_cloud(xyz, attrs)
+        _, coef = oracle_raht(1, make_params(), make_qpset(qp=28), mort, a_s)
+        o, e = oracle_coeff_symbols(coef), emu_coeff_symbols(coef)
+        assert all(np.array_equal(x, y) for x, y in zip(o[:2], e[:2])) and o[3] == e[3]

@@ -281,3 +281,49 @@ def test_live_spherical():
 def _load_liftref_for_test():
     from pcc_testlib import _load_liftref
     return _load_liftref()
+
+
+# --------------------------------------------------------------------------
+# symbol preparation for the entropy coder (row N1)
+
+def _oracle_symbols_for(xyz, attrs, params, qs):
+    mort, a_s, order = sort_cloud(xyz, attrs)
+    orec, ocoef = oracle_raht(1, params, qs, mort, a_s)
+    out = np.empty_like(orec)
+    out[order] = np.clip(orec, 0, 255)
+    return out, oracle_coeff_symbols(ocoef)
+
+
+def test_symbols_golden():
+    """oracle (RAHT + coefficient walk) against the symbol stream decoded from
+    the reference encoder's payload (committed)"""
+    from golden.make_golden import SYMBOL_GOLDEN_CASES
+
+    g = np.load(os.path.join(GOLD, "symbols_golden.npz"))
+    for name, a, qp in SYMBOL_GOLDEN_CASES:
+        rec, (runs, vals, ctx, tail) = _oracle_symbols_for(
+            g[f"{name}/xyz"], g[f"{name}/attrs"], make_params(), make_qpset(qp=qp))
+        assert np.array_equal(runs, g[f"{name}/runs"]) and np.array_equal(vals, g[f"{name}/values"])
+        assert tail == int(g[f"{name}/tail"]) and np.array_equal(rec, g[f"{name}/recon"])
+        assert (ctx is None) == (a == 1)
+
+
+@needs_liftref
+@pytest.mark.parametrize("a", [1, 3])
+def test_live_symbols(a):
+    """the oracle's symbol stream, pushed through the reference's own
+    PCCResidualsEncoder, must give the reference encoder's bitstream byte for
+    byte — through encode() (runs + values) and through encodeSymbol with the
+    oracle's context selectors; and it must be what the reference decoder reads"""
+    for xyz, attrs in (cloud_shell(15000, bits=8, seed=3, a=a), cloud_lidar(15000, seed=2, a=a),
+                       cloud_random(3000, 12, seed=7, a=a, dup_frac=0.2)):
+        for qp, kw in ((34, {}), (10, {}), (46, dict(prediction=0)), (22, dict(haar=1))):
+            params, qs = make_params(**kw), make_qpset(qp=qp)
+            payload, recon = ref_raht_encode_payload(params, qs, xyz, attrs)
+            rec, (runs, vals, ctx, tail) = _oracle_symbols_for(xyz, attrs, params, qs)
+            assert np.array_equal(rec, recon)
+            n = len(xyz)
+            assert ref_symbols_payload(0, runs, vals, ctx, tail, n) == payload
+            assert ref_symbols_payload(1, runs, vals, ctx, tail, n) == payload
+            rr, rv, rt = ref_decode_symbol_stream(payload, n, a)
+            assert np.array_equal(rr, runs) and np.array_equal(rv, vals) and rt == tail
