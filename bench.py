@@ -493,6 +493,38 @@ def run_ours(args):
             lifting["cpu_reference_note"] = ("the reference's own encodeColorsLift on one host core "
                                              "(includes its entropy coding)")
 
+    # ---- the two rows either side of the transform:
+    # spherical positions before it, the entropy coder's symbols after it; one
+    # frame through the host-pointer ABI, reported as an extra key
+    adjacent = None
+    if rank == 0 and not args.no_lifting:
+        try:
+            theta = np.rint(np.tan(np.linspace(-0.43, 0.04, 64)) * (1 << 18)).astype(np.int32)
+            origin, weight = (0, 0, 0), (256, 640, 193128)
+            pb.attr_spherical_positions(origin, theta, weight, xyz)
+            t0 = time.perf_counter()
+            pb.attr_spherical_positions(origin, theta, weight, xyz)
+            sph = time.perf_counter() - t0
+            pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
+            t0 = time.perf_counter()
+            _, runs, _, _, _ = pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
+            sym = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            pb.attr_raht_encode(params, qpset, xyz, rgb)
+            plain = time.perf_counter() - t0
+            adjacent = {
+                "spherical_positions_ms": 1e3 * sph,
+                "spherical_positions_mpoints_per_s": xyz.shape[0] / sph / 1e6,
+                "rgb_encode_with_symbols_ms": 1e3 * sym,
+                "rgb_encode_with_planar_coefficients_ms": 1e3 * plain,
+                "symbols": int(len(runs)),
+                "d2h_bytes_symbols": int(len(runs)) * 16 + rgb.nbytes,
+                "d2h_bytes_planar": 2 * rgb.nbytes,
+                "note": "one 1M-point frame, host-pointer ABI, pageable buffers, wall clock",
+            }
+        except Exception as e:  # an extra: never take the headline down with it
+            adjacent = {"error": str(e)[:200]}
+
     if distributed:
         total_ms, e2e_s = reduce_timing([total_ms, e2e_s], dist, dev)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -546,6 +578,8 @@ def run_ours(args):
             "phase_ms_per_frame_alone": {k: v[0] / prof_steps for k, v in prof.items()},
         }
         line["lifting_path"] = lifting
+        if adjacent is not None:
+            line["adjacent_rows"] = adjacent
         # reported CPU baseline: single N=1 run only (bounded: one frame)
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
