@@ -6,13 +6,14 @@
 //   * one warp per block of siblings; lane = component * 8 + child slot, so
 //     the 2x2x2 block of a colour attribute fills 24 lanes and the three
 //     butterfly stages are __shfl_xor exchanges with lanes 1, 2 and 4 away;
-//     the 18 neighbour look-ups are binary searches run by 18 lanes at once;
+//     the 18 neighbour look-ups are binary searches run by 18 lanes at once
+//     (k_block_geom), and lane i < 19 fetches neighbour i's data;
 //   * everything lives in registers (no per-thread arrays in local memory);
-//   * warps claim blocks in Morton order through a global ticket, a few
-//     consecutive blocks at a time, so a warp may spin on the ready flag of
-//     any earlier block (sub-node prediction reads the reconstruction of
-//     earlier neighbour blocks) and on the zero-run look-back chain (RDOQ)
-//     without any risk of deadlock;
+//   * warps claim blocks in Morton order through a global ticket, one block
+//     at a time, so every lower-numbered block is owned by a running warp: a
+//     warp may wait for the reconstruction slot of any earlier block
+//     (sub-node prediction) and for its zero-run classification (RDOQ)
+//     without any risk of deadlock, whatever the residency;
 //   * blocks with a single child never reach this kernel (PrepFn).
 //
 // Reference: the block loop of uraht_process, tmc3/RAHT.cpp:1306-1808.
@@ -33,7 +34,6 @@ struct WarpBlockArgs {
   int qpLayer;
   int acLayer;
   int predInLvl;
-  int* tz;               // look-back words of this stage, indexed by worklist rank
   const int32_t* worklist;  // block indices in Morton order (null for the root)
   int32_t* geom;            // kGeomStride ints per worklist entry (see k_block_geom)
   const int* count;         // number of worklist entries (device memory)
