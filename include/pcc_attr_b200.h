@@ -374,6 +374,13 @@ int pccb200_attr_raht_encode_symbols(const pccb200_raht_params* params,
                                      uint8_t* ctx_out, int32_t* count_out,
                                      int32_t* tail_run_out);
 
+/* estimateDist2 (tmc3/AttributeEncoder.cpp:1683-1720; per slice from
+ * tmc3/encoder.cpp:1199-1206: abh.attr_dist2_delta = result - aps.dist2).
+ * xyz: N x 3 in coding order.  *shift_bits_out = the reference's return value. */
+int pccb200_estimate_dist2(const int32_t* xyz, int32_t n, int32_t sampling_period,
+                           int32_t search_range, float percentile_estimate,
+                           int32_t* shift_bits_out);
+
 #ifdef __cplusplus
 }
 #endif

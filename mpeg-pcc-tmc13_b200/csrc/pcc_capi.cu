@@ -25,6 +25,7 @@
 #include "raht_pipeline.cuh"
 #include "spherical.cuh"
 #include "symbols.cuh"
+#include "dist2.cuh"
 
 namespace pccb200 {
 
@@ -977,6 +978,30 @@ pccb200_attr_raht_encode_symbols(const pccb200_raht_params* params, const pccb20
     symbols_to_host(ex, dRuns, dValues, dCtx, count, A, zero_runs_out, values_out, ctx_out);
     *count_out = count;
     *tail_run_out = tail;
+    return PCCB200_OK;
+  });
+}
+
+//----------------------------------------------------------------------------
+// estimateDist2 (dist2.cuh)
+
+int
+pccb200_estimate_dist2(const int32_t* xyz, int32_t n, int32_t sampling_period,
+                       int32_t search_range, float percentile_estimate, int32_t* shift_bits_out)
+{
+  if (!xyz || !shift_bits_out || n < 0 || sampling_period < 1 || search_range < 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  if (n < 2) {
+    *shift_bits_out = 0;
+    return PCCB200_OK;
+  }
+  return with_device([&](DeviceExec& ex) -> int {
+    const int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    const int s = run_estimate_dist2(ex, dXyz, n, sampling_period, search_range,
+                                     percentile_estimate);
+    if (s < 0)
+      return fail(PCCB200_ERR_INVALID_ARG, "percentile outside [0, 1)");
+    *shift_bits_out = s;
     return PCCB200_OK;
   });
 }

@@ -84,7 +84,7 @@ EXPORTS = [
     "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
     "pccb200_xyz_to_rpl", "pccb200_offset_and_scale", "pccb200_attr_spherical_positions",
-    "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols",
+    "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols", "pccb200_estimate_dist2",
 ]
 NUM_PHASES = 6
 PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
@@ -411,4 +411,14 @@ def attr_raht_encode_symbols(params, qpset, xyz, attrs, bitdepth=8, qpoffs=None)
         C.byref(tail)))
     s = cnt.value
     return attrs, runs[:s].copy(), values[:s].copy(), (ctx[:s].copy() if a == 3 else None), tail.value
+
+
+def estimate_dist2(xyz, sampling_period=100, search_range=128, percentile=0.85):
+    """estimateDist2 -> shift bits"""
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    out = C.c_int32(0)
+    _check(lib().pccb200_estimate_dist2(_p(xyz, C.c_int32), C.c_int32(xyz.shape[0]),
+                                        C.c_int32(sampling_period), C.c_int32(search_range),
+                                        C.c_float(percentile), C.byref(out)))
+    return out.value
 

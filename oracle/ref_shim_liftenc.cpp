@@ -293,3 +293,17 @@ tmc13ref_symbols_payload(
   memcpy(buf, encoder.arithmeticEncoder.buffer(), len);
   return len;
 }
+
+//============================================================================
+// estimateDist2 (tmc3/AttributeEncoder.cpp:1683-1720), a free function of the
+// included translation unit
+extern "C" int
+tmc13ref_estimate_dist2(
+  const int32_t* xyz, int n, int samplingPeriod, int searchRange, float percentile)
+{
+  PCCPointSet3 cloud;
+  cloud.resize(n);
+  for (int i = 0; i < n; i++)
+    cloud[i] = point_t{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  return estimateDist2(cloud, samplingPeriod, searchRange, percentile);
+}

@@ -6,6 +6,7 @@
 #include "lod_pipeline.cuh"
 #include "spherical.cuh"
 #include "symbols.cuh"
+#include "dist2.cuh"
 #include "raht_pipeline.cuh"
 
 extern "C" int
@@ -81,5 +82,13 @@ emu_coeff_symbols(const int32_t* coeffs, int A, int n, int32_t* runs, int32_t* v
   pccb200::run_coeff_symbols(ex, coeffs, n, A, n, runs, values, ctx, &count, &t);
   *tail = t;
   return count;
+}
+
+// dist2.cuh (host build)
+extern "C" int
+emu_estimate_dist2(const int32_t* xyz, int n, int period, int range, float percentile)
+{
+  HostExec ex;
+  return pccb200::run_estimate_dist2(ex, xyz, n, period, range, percentile);
 }
 

@@ -669,3 +669,25 @@ def ref_decode_symbol_stream(payload, n, a):
         _ptr(values, C.c_int32), C.byref(tail))
     return runs[:cnt].copy(), values[:cnt].copy(), tail.value
 
+
+# --------------------------------------------------------------------------
+# estimateDist2 (row N3, first half)
+
+def _run_dist2(fn, xyz, period, rng_, pct):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    fn.restype = C.c_int
+    return fn(_ptr(xyz, C.c_int32), C.c_int(xyz.shape[0]), C.c_int(period), C.c_int(rng_),
+              C.c_float(pct))
+
+
+def ref_estimate_dist2(xyz, period=100, search_range=128, pct=0.85):
+    return _run_dist2(_load_liftref().tmc13ref_estimate_dist2, xyz, period, search_range, pct)
+
+
+def oracle_estimate_dist2(xyz, period=100, search_range=128, pct=0.85):
+    return _run_dist2(load_oracle().oracle_estimate_dist2, xyz, period, search_range, pct)
+
+
+def emu_estimate_dist2(xyz, period=100, search_range=128, pct=0.85):
+    return _run_dist2(load_emu().emu_estimate_dist2, xyz, period, search_range, pct)
+

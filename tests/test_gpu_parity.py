@@ -432,3 +432,16 @@ def test_entropy_coder_symbols(b200):
             c = (rng.integers(-9, 10, size=(a, n)) * (rng.random((a, n)) < density)).astype(np.int32)
             o, s = oracle_coeff_symbols(c), pb.coeff_symbols(c)
             assert np.array_equal(s[0], o[0]) and np.array_equal(s[1], o[1]) and s[3] == o[3]
+
+
+def test_estimate_dist2(b200):
+    """estimateDist2 (row N3, first half) against the oracle, bench-size frame included"""
+    from test_oracle_vs_reference import _dist2_cases, DIST2_PARAMS
+
+    pb = b200
+    cases = _dist2_cases() + [cloud_lidar(1000000, seed=2)[0]]
+    for xyz in cases:
+        for period, rng_, pct in DIST2_PARAMS:
+            assert pb.estimate_dist2(xyz, period, rng_, pct) == oracle_estimate_dist2(xyz, period, rng_, pct)
+    with pytest.raises(pb.PccB200Error):
+        pb.estimate_dist2(cases[0], 100, 128, 1.0)

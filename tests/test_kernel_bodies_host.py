@@ -167,3 +167,12 @@ def test_symbol_bodies():
         _, coef = oracle_raht(1, make_params(), make_qpset(qp=28), mort, a_s)
         o, e = oracle_coeff_symbols(coef), emu_coeff_symbols(coef)
         assert all(np.array_equal(x, y) for x, y in zip(o[:2], e[:2])) and o[3] == e[3]
+
+
+def test_estimate_dist2_bodies():
+    """dist2.cuh (host build) against the oracle"""
+    from test_oracle_vs_reference import _dist2_cases, DIST2_PARAMS
+
+    for xyz in _dist2_cases():
+        for period, rng_, pct in DIST2_PARAMS:
+            assert emu_estimate_dist2(xyz, period, rng_, pct) == oracle_estimate_dist2(xyz, period, rng_, pct)

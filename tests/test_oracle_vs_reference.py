@@ -327,3 +327,31 @@ def test_live_symbols(a):
             assert ref_symbols_payload(1, runs, vals, ctx, tail, n) == payload
             rr, rv, rt = ref_decode_symbol_stream(payload, n, a)
             assert np.array_equal(rr, runs) and np.array_equal(rv, vals) and rt == tail
+
+
+# --------------------------------------------------------------------------
+# estimateDist2 (row N3, first half)
+
+def _dist2_cases():
+    rng = np.random.default_rng(21)
+    cases = []
+    for n, bits in ((30000, 8), (30000, 12), (5000, 18), (150, 6), (2, 4), (3, 20)):
+        xyz, _ = cloud_random(n, bits, seed=n + bits)
+        mort, _, order = sort_cloud(xyz, np.zeros((len(xyz), 1), dtype=np.int32))
+        cases.append(xyz[order])  # coding order is Morton order after geometry coding
+    cases.append(cloud_lidar(40000, seed=3)[0])
+    cases.append(cloud_shell(40000, bits=10, seed=3)[0])
+    cases.append(np.zeros((500, 3), dtype=np.int32))  # all points coincide
+    cases.append((rng.integers(0, 1 << 20, size=(4000, 3))).astype(np.int32))  # unsorted, far apart
+    return cases
+
+
+DIST2_PARAMS = [(100, 128, 0.85), (1, 4, 0.5), (7, 1, 0.0), (10, 300, 0.99), (1000, 128, 0.85)]
+
+
+@needs_liftref
+def test_live_estimate_dist2():
+    for xyz in _dist2_cases():
+        for period, rng_, pct in DIST2_PARAMS:
+            r = ref_estimate_dist2(xyz, period, rng_, pct)
+            assert oracle_estimate_dist2(xyz, period, rng_, pct) == r, (len(xyz), period, rng_, pct)
