@@ -257,6 +257,17 @@ int pccb200_quant_weights(const pccb200_predictor* preds, int32_t n,
                           const uint32_t* num_points_in_lod, int32_t lod_count,
                           uint64_t* qw_out);
 
+/* computeQuantizationWeights (tmc3/PCCTMC3Common.h:895-921, predicting
+ * transform): the same walk with the per-slot weights neigh_weight[3]
+ * (aps.quant_neigh_weight) instead of the predictors' own. */
+int pccb200_quant_weights_fixed(const pccb200_predictor* preds, int32_t n,
+                                const uint32_t* num_points_in_lod, int32_t lod_count,
+                                const int32_t neigh_weight[3], uint64_t* qw_out);
+/* computeQuantizationWeightsScalable (tmc3/PCCTMC3Common.h:858-891). */
+int pccb200_quant_weights_scalable(const uint32_t* num_points_in_lod, int32_t lod_count,
+                                   int64_t num_points, int32_t min_geom_node_size_log2,
+                                   int32_t n, uint64_t* qw_out);
+
 /* attrs_inout: N x A int64 in predictor order (values already << 8).
  * Forward: for lod = lod_count-1 .. 1: predict then update
  * (tmc3/AttributeEncoder.cpp:1408-1415).  Inverse: lod = 1 .. lod_count-1:

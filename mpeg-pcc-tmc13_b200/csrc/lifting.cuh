@@ -53,17 +53,29 @@ struct LodCheckFn {
   }
 };
 
+// neighbour weight j of a predictor: its own (lifting, PCCTMC3Common.h:828-854)
+// or the fixed per-slot weight of the predicting transform
+// (computeQuantizationWeights, PCCTMC3Common.h:895-921)
+struct NeighWeights {
+  int32_t fixed[3];
+  int useFixed;
+  PCC_HD uint64_t of(const pccb200_predictor& p, uint32_t j) const
+  {
+    return useFixed ? uint64_t(int64_t(fixed[j])) : uint64_t(p.weight[j]);
+  }
+};
+
 struct QuantWeightLodFn {
   const pccb200_predictor* preds;
   uint64_t* qw;
   int64_t start;
+  NeighWeights nw;
   PCC_HD void operator()(int64_t i) const
   {
     const pccb200_predictor& p = preds[start + i];
     const uint64_t w = qw[start + i];
     for (uint32_t j = 0; j < p.neighbor_count; j++)
-      atomic_add_u64(&qw[p.predictor_index[j]],
-                     div_exp2_round_half_inf_u(uint64_t(p.weight[j]) * w, 8));
+      atomic_add_u64(&qw[p.predictor_index[j]], div_exp2_round_half_inf_u(nw.of(p, j) * w, 8));
   }
 };
 
@@ -72,16 +84,25 @@ struct QuantWeightSeqFn {
   const pccb200_predictor* preds;
   uint64_t* qw;
   int64_t start, end;
+  NeighWeights nw;
   PCC_HD void operator()(int64_t) const
   {
     for (int64_t i = end - 1; i >= start; i--) {
       const pccb200_predictor& p = preds[i];
       const uint64_t w = qw[i];
       for (uint32_t j = 0; j < p.neighbor_count; j++)
-        qw[p.predictor_index[j]] +=
-          div_exp2_round_half_inf_u(uint64_t(p.weight[j]) * w, 8);
+        qw[p.predictor_index[j]] += div_exp2_round_half_inf_u(nw.of(p, j) * w, 8);
     }
   }
+};
+
+// computeQuantizationWeightsScalable (PCCTMC3Common.h:858-891): one constant
+// per level of detail
+struct QuantWeightScalableFn {
+  uint64_t* qw;
+  int64_t start;
+  uint64_t value;
+  PCC_HD void operator()(int64_t i) const { qw[start + i] = value; }
 };
 
 struct LiftPredictFn {
@@ -347,8 +368,15 @@ struct ScatterReconFn {  // out[indexes[i]] = clip(divExp2RoundHalfInf(in[i], 8)
 template<class Exec>
 int
 run_quant_weights(Exec& ex, const pccb200_predictor* preds, int64_t n,
-                  const uint32_t* numPointsInLod, int lodCount, uint64_t* qw)
+                  const uint32_t* numPointsInLod, int lodCount, uint64_t* qw,
+                  const int32_t* fixedNeighWeight = nullptr)
 {
+  NeighWeights nw{{0, 0, 0}, 0};
+  if (fixedNeighWeight) {
+    for (int j = 0; j < 3; j++)
+      nw.fixed[j] = fixedNeighWeight[j];
+    nw.useFixed = 1;
+  }
   ex.phase(5);
   ex.foreach(n, FillU64Fn{qw, uint64_t(1) << 8});
   int* dFlags = ex.template alloc<int>(size_t(lodCount) + 1);
@@ -370,11 +398,32 @@ run_quant_weights(Exec& ex, const pccb200_predictor* preds, int64_t n,
     int64_t s = l ? numPointsInLod[l - 1] : 0;
     int64_t e = numPointsInLod[l];
     if (flags[l])
-      ex.foreach(1, QuantWeightSeqFn{preds, qw, s, e});
+      ex.foreach(1, QuantWeightSeqFn{preds, qw, s, e, nw});
     else
-      ex.foreach(e - s, QuantWeightLodFn{preds, qw, s});
+      ex.foreach(e - s, QuantWeightLodFn{preds, qw, s, nw});
   }
   return PCCB200_OK;
+}
+
+template<class Exec>
+int
+run_quant_weights_scalable(Exec& ex, const uint32_t* numPointsInLod, int lodCount,
+                           uint64_t numPoints, int minGeomNodeSizeLog2, int64_t n, uint64_t* qw)
+{
+  ex.phase(5);
+  int64_t prevEnd = 0;
+  for (int l = 0; l < lodCount; l++) {
+    const int64_t s = l ? numPointsInLod[l - 1] : 0;
+    const int64_t e = numPointsInLod[l];
+    if (s != prevEnd || e < s || e > n || e == 0)
+      return PCCB200_ERR_INVALID_ARG;
+    prevEnd = e;
+    uint64_t v = (numPoints / uint64_t(e)) << 8;
+    if (!minGeomNodeSizeLog2 && l == lodCount - 1)
+      v = uint64_t(1) << 8;
+    ex.foreach(e - s, QuantWeightScalableFn{qw, s, v});
+  }
+  return prevEnd == n ? PCCB200_OK : PCCB200_ERR_INVALID_ARG;
 }
 
 template<class Exec>

@@ -1006,4 +1006,43 @@ pccb200_estimate_dist2(const int32_t* xyz, int32_t n, int32_t sampling_period,
   });
 }
 
+//----------------------------------------------------------------------------
+// the other two quantisation-weight derivations (lifting.cuh)
+
+int
+pccb200_quant_weights_fixed(const pccb200_predictor* preds, int32_t n,
+                            const uint32_t* num_points_in_lod, int32_t lod_count,
+                            const int32_t neigh_weight[3], uint64_t* qw_out)
+{
+  if (!preds || !num_points_in_lod || !neigh_weight || !qw_out || n <= 0 || lod_count <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    pccb200_predictor* dP = to_device(ex, preds, size_t(n));
+    uint64_t* dQw = ex.alloc<uint64_t>(n);
+    int rc = run_quant_weights(ex, dP, n, num_points_in_lod, lod_count, dQw, neigh_weight);
+    if (rc != PCCB200_OK)
+      return fail(rc, "numPointsInLod does not partition [0, n)");
+    to_host(ex, qw_out, dQw, size_t(n));
+    return PCCB200_OK;
+  });
+}
+
+int
+pccb200_quant_weights_scalable(const uint32_t* num_points_in_lod, int32_t lod_count,
+                               int64_t num_points, int32_t min_geom_node_size_log2, int32_t n,
+                               uint64_t* qw_out)
+{
+  if (!num_points_in_lod || !qw_out || n <= 0 || lod_count <= 0 || num_points < 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    uint64_t* dQw = ex.alloc<uint64_t>(n);
+    int rc = run_quant_weights_scalable(ex, num_points_in_lod, lod_count, uint64_t(num_points),
+                                        min_geom_node_size_log2, n, dQw);
+    if (rc != PCCB200_OK)
+      return fail(rc, "numPointsInLod does not partition [0, n)");
+    to_host(ex, qw_out, dQw, size_t(n));
+    return PCCB200_OK;
+  });
+}
+
 }  // extern "C"

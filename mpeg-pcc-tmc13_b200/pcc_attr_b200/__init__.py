@@ -85,6 +85,7 @@ EXPORTS = [
     "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
     "pccb200_xyz_to_rpl", "pccb200_offset_and_scale", "pccb200_attr_spherical_positions",
     "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols", "pccb200_estimate_dist2",
+    "pccb200_quant_weights_fixed", "pccb200_quant_weights_scalable",
 ]
 NUM_PHASES = 6
 PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
@@ -421,4 +422,27 @@ def estimate_dist2(xyz, sampling_period=100, search_range=128, percentile=0.85):
                                         C.c_int32(sampling_period), C.c_int32(search_range),
                                         C.c_float(percentile), C.byref(out)))
     return out.value
+
+
+def quant_weights_fixed(preds, num_points_in_lod, neigh_weight):
+    """computeQuantizationWeights (predicting transform) -> qw[N]"""
+    preds = np.ascontiguousarray(preds)
+    npl = np.ascontiguousarray(num_points_in_lod, dtype=np.uint32)
+    n = preds.shape[0]
+    qw = np.zeros(n, dtype=np.uint64)
+    _check(lib().pccb200_quant_weights_fixed(
+        C.cast(preds.ctypes.data, C.POINTER(Predictor)), C.c_int32(n), _p(npl, C.c_uint32),
+        C.c_int32(npl.size), _i3(neigh_weight), _p(qw, C.c_uint64)))
+    return qw
+
+
+def quant_weights_scalable(num_points_in_lod, num_points, min_geom_node_size_log2):
+    """computeQuantizationWeightsScalable -> qw[N], N = num_points_in_lod[-1]"""
+    npl = np.ascontiguousarray(num_points_in_lod, dtype=np.uint32)
+    n = int(npl[-1])
+    qw = np.zeros(n, dtype=np.uint64)
+    _check(lib().pccb200_quant_weights_scalable(
+        _p(npl, C.c_uint32), C.c_int32(npl.size), C.c_int64(num_points),
+        C.c_int32(min_geom_node_size_log2), C.c_int32(n), _p(qw, C.c_uint64)))
+    return qw
 

@@ -195,3 +195,32 @@ oracle_lift_quant(int forward, const pccb200_qpset* qs, const int32_t* qpo, cons
     a[2] = orc_div_exp2_half_inf(scaled * iqw, 40);
   }
 }
+
+/* computeQuantizationWeights, tmc3/PCCTMC3Common.h:895-921 (predicting transform) */
+void
+oracle_quant_weights_fixed(const pccb200_predictor* preds, int n, const int32_t neigh_weight[3],
+                           uint64_t* qw)
+{
+  for (int i = 0; i < n; i++)
+    qw[i] = 1u << 8;
+  for (int i = n - 1; i >= 0; i--) {
+    const pccb200_predictor* p = &preds[i];
+    uint64_t w = qw[i];
+    for (uint32_t j = 0; j < p->neighbor_count; j++)
+      qw[p->predictor_index[j]] += orc_div_exp2_half_inf_u((uint64_t)(int64_t)neigh_weight[j] * w, 8);
+  }
+}
+
+/* computeQuantizationWeightsScalable, tmc3/PCCTMC3Common.h:858-891 */
+void
+oracle_quant_weights_scalable(const uint32_t* npl, int lod_count, uint64_t num_points,
+                              int min_geom_node_size_log2, uint64_t* qw)
+{
+  for (int l = 0; l < lod_count; l++) {
+    uint32_t s = l ? npl[l - 1] : 0, e = npl[l];
+    uint64_t v = (num_points / npl[l]) << 8;
+    for (uint32_t i = s; i < e; i++)
+      qw[i] = (!min_geom_node_size_log2 && l == lod_count - 1) ? (uint64_t)1 << 8 : v;
+  }
+}
+

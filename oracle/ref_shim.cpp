@@ -239,6 +239,31 @@ tmc13ref_quant_weights(const pccb200_predictor* preds, int n, uint64_t* qw)
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+void
+tmc13ref_quant_weights_fixed(
+  const pccb200_predictor* preds, int n, const int32_t neighWeight[3], uint64_t* qw)
+{
+  std::vector<PCCPredictor> predictors;
+  mkPredictors(preds, n, predictors);
+  std::vector<uint64_t> w;
+  computeQuantizationWeights(
+    predictors, w, Vec3<int32_t>(neighWeight[0], neighWeight[1], neighWeight[2]));
+  std::copy(w.begin(), w.end(), qw);
+}
+
+void
+tmc13ref_quant_weights_scalable(
+  const pccb200_predictor* preds, int n, const uint32_t* npl, int lodCount, uint64_t numPoints,
+  int minGeomNodeSizeLog2, uint64_t* qw)
+{
+  std::vector<PCCPredictor> predictors;
+  mkPredictors(preds, n, predictors);
+  std::vector<uint32_t> perLod(npl, npl + lodCount);
+  std::vector<uint64_t> w;
+  computeQuantizationWeightsScalable(predictors, perLod, numPoints, minGeomNodeSizeLog2, w);
+  std::copy(w.begin(), w.end(), qw);
+}
+
 double
 tmc13ref_lift(
   int forward,

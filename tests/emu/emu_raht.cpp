@@ -92,3 +92,19 @@ emu_estimate_dist2(const int32_t* xyz, int n, int period, int range, float perce
   return pccb200::run_estimate_dist2(ex, xyz, n, period, range, percentile);
 }
 
+// the other quantisation-weight derivations of lifting.cuh (host build)
+extern "C" int
+emu_quant_weights_fixed(const pccb200_predictor* preds, int n, const uint32_t* npl, int lodCount,
+                        const int32_t* neighWeight, uint64_t* qw)
+{
+  HostExec ex;
+  return pccb200::run_quant_weights(ex, preds, n, npl, lodCount, qw, neighWeight);
+}
+extern "C" int
+emu_quant_weights_scalable(const uint32_t* npl, int lodCount, uint64_t numPoints, int minLog2, int n,
+                           uint64_t* qw)
+{
+  HostExec ex;
+  return pccb200::run_quant_weights_scalable(ex, npl, lodCount, numPoints, minLog2, n, qw);
+}
+

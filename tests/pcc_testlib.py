@@ -691,3 +691,62 @@ def oracle_estimate_dist2(xyz, period=100, search_range=128, pct=0.85):
 def emu_estimate_dist2(xyz, period=100, search_range=128, pct=0.85):
     return _run_dist2(load_emu().emu_estimate_dist2, xyz, period, search_range, pct)
 
+
+# --------------------------------------------------------------------------
+# the other two quantisation-weight derivations (row L5)
+
+def ref_quant_weights_fixed(preds, neigh_weight):
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    load_ref().tmc13ref_quant_weights_fixed(_pp(preds), C.c_int(preds.shape[0]), _i3(neigh_weight),
+                                            _ptr(qw, C.c_uint64))
+    return qw
+
+
+def oracle_quant_weights_fixed(preds, neigh_weight):
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    load_oracle().oracle_quant_weights_fixed(_pp(preds), C.c_int(preds.shape[0]),
+                                             _i3(neigh_weight), _ptr(qw, C.c_uint64))
+    return qw
+
+
+def emu_quant_weights_fixed(preds, npl, neigh_weight):
+    npl = np.ascontiguousarray(npl, dtype=np.uint32)
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    lib = load_emu()
+    lib.emu_quant_weights_fixed.restype = C.c_int
+    rc = lib.emu_quant_weights_fixed(_pp(preds), C.c_int(preds.shape[0]), _ptr(npl, C.c_uint32),
+                                     C.c_int(npl.size), _i3(neigh_weight), _ptr(qw, C.c_uint64))
+    assert rc == 0
+    return qw
+
+
+def ref_quant_weights_scalable(preds, npl, num_points, min_log2):
+    npl = np.ascontiguousarray(npl, dtype=np.uint32)
+    qw = np.zeros(preds.shape[0], dtype=np.uint64)
+    load_ref().tmc13ref_quant_weights_scalable(
+        _pp(preds), C.c_int(preds.shape[0]), _ptr(npl, C.c_uint32), C.c_int(npl.size),
+        C.c_uint64(num_points), C.c_int(min_log2), _ptr(qw, C.c_uint64))
+    return qw
+
+
+def oracle_quant_weights_scalable(npl, num_points, min_log2):
+    npl = np.ascontiguousarray(npl, dtype=np.uint32)
+    qw = np.zeros(int(npl[-1]), dtype=np.uint64)
+    load_oracle().oracle_quant_weights_scalable(_ptr(npl, C.c_uint32), C.c_int(npl.size),
+                                                C.c_uint64(num_points), C.c_int(min_log2),
+                                                _ptr(qw, C.c_uint64))
+    return qw
+
+
+def emu_quant_weights_scalable(npl, num_points, min_log2):
+    npl = np.ascontiguousarray(npl, dtype=np.uint32)
+    n = int(npl[-1])
+    qw = np.zeros(n, dtype=np.uint64)
+    lib = load_emu()
+    lib.emu_quant_weights_scalable.restype = C.c_int
+    rc = lib.emu_quant_weights_scalable(_ptr(npl, C.c_uint32), C.c_int(npl.size),
+                                        C.c_uint64(num_points), C.c_int(min_log2), C.c_int(n),
+                                        _ptr(qw, C.c_uint64))
+    assert rc == 0
+    return qw
+

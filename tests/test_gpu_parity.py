@@ -445,3 +445,23 @@ def test_estimate_dist2(b200):
             assert pb.estimate_dist2(xyz, period, rng_, pct) == oracle_estimate_dist2(xyz, period, rng_, pct)
     with pytest.raises(pb.PccB200Error):
         pb.estimate_dist2(cases[0], 100, 128, 1.0)
+
+
+def test_quant_weight_variants(b200):
+    """computeQuantizationWeights (predicting transform, fixed per-slot weights;
+    levels of detail that reference themselves run the ordered body) and
+    computeQuantizationWeightsScalable, against the oracle"""
+    from test_oracle_vs_reference import _qw_structures
+
+    pb = b200
+    structs = _qw_structures()
+    xyz, _ = cloud_shell(300000, bits=10, seed=12)
+    p, idx, npl = oracle_lod_build(make_lod_params(levels=10), xyz)
+    structs.append((p, npl))
+    for preds, npl in structs:
+        for nw in ((256, 128, 64), (8192, 0, 5)):
+            assert np.array_equal(pb.quant_weights_fixed(preds, npl, nw), oracle_quant_weights_fixed(preds, nw))
+        n = len(preds)
+        for num_points, min_log2 in ((n, 0), (3 * n + 7, 1)):
+            assert np.array_equal(pb.quant_weights_scalable(npl, num_points, min_log2),
+                                  oracle_quant_weights_scalable(npl, num_points, min_log2))

@@ -176,3 +176,16 @@ def test_estimate_dist2_bodies():
     for xyz in _dist2_cases():
         for period, rng_, pct in DIST2_PARAMS:
             assert emu_estimate_dist2(xyz, period, rng_, pct) == oracle_estimate_dist2(xyz, period, rng_, pct)
+
+
+def test_quant_weight_variant_bodies():
+    """lifting.cuh (host build): fixed-weight and scalable quantisation weights"""
+    from test_oracle_vs_reference import _qw_structures
+
+    for preds, npl in _qw_structures():
+        for nw in ((256, 128, 64), (8192, 0, 5)):
+            assert np.array_equal(emu_quant_weights_fixed(preds, npl, nw), oracle_quant_weights_fixed(preds, nw))
+        n = len(preds)
+        for num_points, min_log2 in ((n, 0), (3 * n + 7, 1)):
+            assert np.array_equal(emu_quant_weights_scalable(npl, num_points, min_log2),
+                                  oracle_quant_weights_scalable(npl, num_points, min_log2))

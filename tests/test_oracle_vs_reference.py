@@ -355,3 +355,29 @@ def test_live_estimate_dist2():
         for period, rng_, pct in DIST2_PARAMS:
             r = ref_estimate_dist2(xyz, period, rng_, pct)
             assert oracle_estimate_dist2(xyz, period, rng_, pct) == r, (len(xyz), period, rng_, pct)
+
+
+# --------------------------------------------------------------------------
+# quantisation weights of the predicting transform and of scalable lifting (row L5)
+
+def _qw_structures():
+    out = [synth_predictors(n, lods, seed=n) for n, lods in ((5000, 6), (40000, 9), (37, 3))]
+    # real LoD builds, with predictors that reference their own level of detail
+    for kw in (dict(decimation=0, skip_layers=0, intra_range=128, inter_range=128, blending=1),
+               dict(decimation=1, skip_layers=0, intra_range=16, inter_range=16, period=3),
+               dict()):
+        xyz, _ = cloud_shell(15000, bits=8, seed=9)
+        p, idx, npl = oracle_lod_build(make_lod_params(**dict(kw, levels=8)), xyz)
+        out.append((p, npl))
+    return out
+
+
+@needs_ref
+def test_live_quant_weight_variants():
+    for preds, npl in _qw_structures():
+        for nw in ((256, 128, 64), (1, 1, 1), (8192, 0, 5)):
+            assert np.array_equal(ref_quant_weights_fixed(preds, nw), oracle_quant_weights_fixed(preds, nw))
+        n = len(preds)
+        for num_points, min_log2 in ((n, 0), (n, 2), (3 * n + 7, 1)):
+            assert np.array_equal(ref_quant_weights_scalable(preds, npl, num_points, min_log2),
+                                  oracle_quant_weights_scalable(npl, num_points, min_log2))
