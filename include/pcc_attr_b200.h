@@ -91,7 +91,12 @@ typedef struct pccb200_qpset {
 void pccb200_raht_params_default(pccb200_raht_params* p);
 
 /* Derive the 19 + 12 prediction weights from the 5 signalled ones
- * (RahtPredictionParams::setPredictionWeights, tmc3/hls.h:456-465). */
+ * (RahtPredictionParams::setPredictionWeights, tmc3/hls.h:456-465).
+ * The reference normalises a prediction by a 64-entry reciprocal table indexed
+ * by the sum of the weights that reached a child (tmc3/RAHT.cpp:445-451,
+ * 567-570); a weight set with w[0] + 3*max(w[1],w[3]) + 3*max(w[2],w[4]) > 64
+ * makes it read past that table.  This library evaluates the table's formula,
+ * round(32768 / sum), for any sum: identical wherever the reference is defined. */
 void pccb200_raht_set_prediction_weights(pccb200_raht_params* p,
                                          const int32_t w[5]);
 
