@@ -52,6 +52,10 @@ def main():
             ov, orr, ol = oracle_lift_encode(lp, qs, lcp, xyz, at)
             ev, er, el = emu_attr_lift(1, lp, qs, lcp, xyz, at)
             ok = np.array_equal(ev, ov) and np.array_equal(er, orr) and (not (a == 3 and lcp) or np.array_equal(el, ol))
+            if ok and liftref_available():  # the reference's own lifting encoder bodies
+                rv, rrec, rl = ref_lift_encode(lp, qs, lcp, xyz, at)
+                ok = np.array_equal(rv, ov) and np.array_equal(rrec, orr) and (
+                    not (a == 3 and lcp) or np.array_equal(rl, ol))
         if not ok:
             bad += 1
             print("MISMATCH case", i, "n", len(xyz), kw, "lifting", lifting)
