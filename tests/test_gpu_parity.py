@@ -465,3 +465,16 @@ def test_quant_weight_variants(b200):
         for num_points, min_log2 in ((n, 0), (3 * n + 7, 1)):
             assert np.array_equal(pb.quant_weights_scalable(npl, num_points, min_log2),
                                   oracle_quant_weights_scalable(npl, num_points, min_log2))
+
+
+def test_fuzz_slice_gpu(b200):
+    """a seeded slice of tools/fuzz_gpu.py: the CUDA path against the oracle on
+    random points of the parameter space (transform, attribute level, symbol
+    stream, LoD build, lifting coder)"""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_gpu.py"), "90", "50", "7"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "raht 90 cases, 0 mismatches; lod/lifting 50 cases, 0 mismatches" in r.stdout
