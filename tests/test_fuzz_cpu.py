@@ -1,4 +1,5 @@
-"""Seeded slices of the CPU fuzzers (tools/fuzz_cpu.py, tools/fuzz_lod_cpu.py):
+"""Seeded slices of the CPU fuzzers (tools/fuzz_cpu.py, tools/fuzz_lod_cpu.py,
+tools/fuzz_misc_cpu.py):
 compiled reference == oracle == kernel bodies (host build) over random points
 of the parameter space.  The full sweeps are developer tools; these keep a few
 dozen configurations in the regular suite."""
@@ -17,7 +18,8 @@ needs_ref = pytest.mark.skipif(
 
 
 @needs_ref
-@pytest.mark.parametrize("tool,cases,seed", [("fuzz_cpu.py", 40, 101), ("fuzz_lod_cpu.py", 30, 102)])
+@pytest.mark.parametrize("tool,cases,seed", [("fuzz_cpu.py", 40, 101), ("fuzz_lod_cpu.py", 30, 102),
+                                             ("fuzz_misc_cpu.py", 30, 103)])
 def test_fuzz_slice(tool, cases, seed):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), str(cases), str(seed)],
                        capture_output=True, text=True, timeout=600)
