@@ -77,15 +77,29 @@ def workload_config():
     }
 
 
-def make_frame(seed):
-    from pcc_attr_b200.synth import cloud_lidar
+TEXTURE_RGB = 16    # +- amplitude of the per-point texture of the headline frame
+TEXTURE_REFL = 24
+
+
+def make_frame(seed, textured=True):
+    """One frame of configs[1].  textured=False is round 1's smooth attribute
+    field (0.1 % of the coefficients non-zero at qp 34); textured=True adds
+    per-point texture so that the quantiser and the RDOQ zero-run chain are
+    exercised like on real content (12-27 % of the positions
+    quantise to 1 or 2)."""
+    from pcc_attr_b200.synth import cloud_lidar, texture
 
     xyz, rgb = cloud_lidar(N_POINTS, seed=seed, a=3)
     rng = np.random.default_rng(seed + 1000)
     # reflectance: range-dependent intensity + noise
     r = np.linalg.norm(xyz.astype(np.float64), axis=1)
     refl = np.clip(200.0 * np.exp(-r / (r.max() + 1)) + rng.integers(-6, 7, size=r.shape), 0, 255)
-    return xyz, rgb.astype(np.int32), np.rint(refl).astype(np.int32)[:, None]
+    rgb = rgb.astype(np.int32)
+    refl = np.rint(refl).astype(np.int32)[:, None]
+    if textured:
+        rgb = texture(rgb, TEXTURE_RGB, seed + 2000)
+        refl = texture(refl, TEXTURE_REFL, seed + 3000)
+    return xyz, rgb, refl
 
 
 def make_pods(pb):
@@ -118,7 +132,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "1000"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -201,6 +215,49 @@ def cpu_frame_seconds(run, params, qpset, frame):
     run(params, qpset, xyz, rgb)
     run(params, qpset, xyz, refl)
     return time.perf_counter() - t0
+
+
+def physical_cores():
+    """number of physical cores of the host (hyper-threads counted once)"""
+    try:
+        seen, phys, core = set(), None, None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("physical id"):
+                phys = ln.split(":")[1].strip()
+            elif ln.startswith("core id"):
+                core = ln.split(":")[1].strip()
+            elif not ln.strip():
+                if phys is not None and core is not None:
+                    seen.add((phys, core))
+                phys = core = None
+        if seen:
+            return len(seen)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Bind this rank's threads to the CPUs of its GPU's NUMA node (the launch
+    and staging threads of 8 ranks otherwise wander over both sockets)."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (
+            pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def host_cpu_model():

@@ -185,7 +185,19 @@ int pccb200_time_end(double* ms_out);
 
 /* As pccb200_attr_raht_encode_slices / a decode counterpart, but every array
  * pointer is a DEVICE pointer on the selected device; slice_offsets stays a
- * host array.  Complete on return. */
+ * host array.
+ *
+ * Stream ordering: the library works on its own non-blocking streams, which
+ * are NOT ordered with any stream of the caller.  Everything that produces
+ * the input buffers must have completed before the call (synchronise the
+ * producing stream, or an event recorded on it, first); the outputs are
+ * complete when the call returns, so any stream may consume them afterwards.
+ *
+ * Concurrency: for calls from several host threads to overlap on the device
+ * each lane needs its own hardware queue; set CUDA_DEVICE_MAX_CONNECTIONS=32
+ * in the process environment before the CUDA context is created (with the
+ * default of 8 a long dataflow kernel blocks the short kernels of a lane
+ * that shares its queue).  The library does not touch the environment. */
 int pccb200_attr_raht_encode_slices_dev(const pccb200_raht_params* params,
                                         const pccb200_qpset* qpset,
                                         const int32_t* d_point_qp_offsets,
@@ -208,9 +220,12 @@ int pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
  * the call's stream).  Phases: 0 Morton keys + radix sort, 1 tree build
  * (histogram, compaction, leaf / merge kernels), 2 block transform (the
  * top-down dataflow kernels), 3 duplicate tail + write-back, 4 gather /
- * scatter / clip, 5 lifting passes.  pccb200_profile_read returns the
- * accumulated milliseconds and launch counts since the last reset. */
-#define PCCB200_NUM_PHASES 6
+ * scatter / clip, 5 lifting passes, 6 block geometry (worklists, neighbour
+ * searches, qp descent: shared by everything that codes the same positions),
+ * 7 block schedule (dependency levels + sort into wavefront order).
+ * pccb200_profile_read returns the accumulated milliseconds and launch
+ * counts since the last reset. */
+#define PCCB200_NUM_PHASES 8
 void pccb200_profile_enable(int enable);
 void pccb200_profile_reset(void);
 void pccb200_profile_read(double ms_out[PCCB200_NUM_PHASES],

@@ -50,30 +50,38 @@ class Arena {
 public:
   ~Arena() { release(); }
 
+  // Chunks are kept from call to call and filled in order; a call that needs
+  // more gets a new chunk (cudaMalloc does not disturb running kernels).
   void* alloc(size_t bytes)
   {
     bytes = (bytes + 255) & ~size_t(255);
-    if (chunks_.empty() || used_ + bytes > chunks_.back().size) {
+    while (cur_ < chunks_.size() && used_ + bytes > chunks_[cur_].size) {
+      cur_++;
+      used_ = 0;
+    }
+    if (cur_ == chunks_.size()) {
       size_t want = bytes > nextSize_ ? bytes : nextSize_;
       void* p = nullptr;
       PCC_CUDA_CHECK(cudaMalloc(&p, want));
       chunks_.push_back({p, want});
-      total_ += want;
       used_ = 0;
     }
-    void* r = static_cast<char*>(chunks_.back().ptr) + used_;
+    void* r = static_cast<char*>(chunks_[cur_].ptr) + used_;
     used_ += bytes;
     high_ += bytes;
     return r;
   }
 
-  // start of a call: fold everything into one chunk big enough for the
-  // largest call seen so far
-  void reset()
+  // Start of a call.  mayFree: no other call is in flight, so the chunks may
+  // be folded into one big enough for the largest call seen so far (cudaFree
+  // synchronises the device: it would stall the dataflow kernels of the other
+  // lanes in the middle of their polling, so it is never done under load).
+  void reset(bool mayFree)
   {
     if (high_ > peak_)
       peak_ = high_;
-    if (chunks_.size() > 1 || (chunks_.size() == 1 && chunks_[0].size < peak_)) {
+    if (mayFree
+        && (chunks_.size() > 1 || (chunks_.size() == 1 && chunks_[0].size < peak_))) {
       release();
     }
     if (chunks_.empty() && peak_) {
@@ -81,8 +89,8 @@ public:
       size_t want = peak_ + (peak_ >> 3) + (1 << 20);
       PCC_CUDA_CHECK(cudaMalloc(&p, want));
       chunks_.push_back({p, want});
-      total_ = want;
     }
+    cur_ = 0;
     used_ = 0;
     high_ = 0;
   }
@@ -92,7 +100,7 @@ public:
     for (auto& c : chunks_)
       cudaFree(c.ptr);
     chunks_.clear();
-    total_ = 0;
+    cur_ = 0;
     used_ = 0;
   }
 
@@ -102,8 +110,8 @@ private:
     size_t size;
   };
   std::vector<Chunk> chunks_;
+  size_t cur_ = 0;
   size_t used_ = 0;
-  size_t total_ = 0;
   size_t high_ = 0;
   size_t peak_ = 0;
   size_t nextSize_ = size_t(64) << 20;
@@ -300,7 +308,10 @@ struct Profiler {
   }
 };
 
-enum Phase { kPhaseSort = 0, kPhaseTree, kPhaseBlock, kPhaseTail, kPhaseGather, kPhaseLift };
+enum Phase {
+  kPhaseSort = 0, kPhaseTree, kPhaseBlock, kPhaseTail, kPhaseGather, kPhaseLift, kPhaseGeom,
+  kPhaseOrder
+};
 
 struct DeviceExec {
   cudaStream_t stream = nullptr;
@@ -465,6 +476,45 @@ struct DeviceExec {
     PCC_CUDA_CHECK(cudaGetLastError());
   }
 
+
+  // Persistent grid of the block kernels for a stage of nBlocks blocks: the
+  // resident CTAs of the machine, shared among the calls in flight.
+  int64_t block_grid(int64_t nBlocks) const
+  {
+    static const int perSM = [] {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_block_warp, kWarpBlockThreads, 0)
+          != cudaSuccess)
+        v = 0;
+      return v < 1 ? 1 : v;
+    }();
+    const int64_t perCta = kWarpBlockThreads / 32;
+    int64_t blocks = (nBlocks + perCta - 1) / perCta;
+    // calls in flight share the machine: the persistent grid of each takes
+    // its part (sampled at launch time).  Together the persistent grids of the
+    // calls in flight fill the machine once (measured best on the bench: 50 %
+    // and 75 % were slower, and so were more resident warps per SM); the short
+    // kernels of other calls (sort, tree build, PrepFn ...) get their turn as
+    // CTAs retire between stages.
+    const int inFlight = activeCalls ? activeCalls->load() : 1;
+    int64_t cap = int64_t(numSMs) * perSM;
+    static const int capShare = [] {  // percent of the machine all calls in flight may hold
+      const char* e = getenv("PCCB200_BLOCK_SHARE");
+      return e ? atoi(e) : 100;
+    }();
+    if (inFlight > 1)
+      cap = cap * capShare / (100 * inFlight);
+    static const int envCap = [] {
+      const char* e = getenv("PCCB200_BLOCK_GRID");
+      return e ? atoi(e) : 0;
+    }();
+    if (envCap > 0)
+      cap = envCap;
+    if (cap < 8)
+      cap = 8;
+    return blocks > cap ? cap : blocks;
+  }
+
   // One top-down stage.  Default: PrepFn (single-child blocks, qp descent) ->
   // worklist of the transforming blocks -> warp-cooperative dataflow kernel.
   // PCCB200_BLOCK_KERNEL=thread selects the thread-per-block body (BlockFn)
@@ -492,7 +542,7 @@ struct DeviceExec {
         foreach(1, TzCarryFn{fn.tz, nullptr, int(nBlocks), tzNext});
       return;
     }
-    WarpBlockArgs a;
+    WarpBlockArgs a = {};
     a.cfg = fn.cfg;
     a.qt = fn.qt;
     a.S = fn.S;
@@ -504,11 +554,6 @@ struct DeviceExec {
     a.acLayer = fn.acLayer;
     a.predInLvl = fn.predInLvl;
     raht_ab(1, 1, a.ab11a, a.ab11b);
-    static const int experiment = [] {
-      const char* e = getenv("PCCB200_EXPERIMENT");
-      return e ? atoi(e) : 0;
-    }();
-    a.experiment = experiment;
     int* dCount = alloc<int>(1);
     if (root) {
       int one = 1;
@@ -548,40 +593,8 @@ struct DeviceExec {
       g_launchCount++;
     }
     PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
-    static int perSM = 0;
-    if (!perSM) {
-      PCC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &perSM, k_block_warp, kWarpBlockThreads, 0));
-      if (perSM < 1)
-        perSM = 1;
-    }
-    const int64_t perCta = int64_t(kWarpBlockThreads / 32) * kWarpBlockChunk;
-    int64_t blocks = (nBlocks + perCta - 1) / perCta;
-    // calls in flight share the machine: the persistent grid of each takes
-    // its part (sampled at launch time)
-    const int inFlight = activeCalls ? activeCalls->load() : 1;
-    // Together the persistent grids of the calls in flight fill the machine
-    // once (measured best on the bench: 50 % and 75 % were slower, and so were
-    // more resident warps per SM); the short kernels of other calls (sort,
-    // tree build, PrepFn ...) get their turn as CTAs retire between stages.
-    int64_t cap = int64_t(numSMs) * perSM;
-    static const int capShare = [] {  // percent of the machine all calls in flight may hold
-      const char* e = getenv("PCCB200_BLOCK_SHARE");
-      return e ? atoi(e) : 100;
-    }();
-    if (inFlight > 1)
-      cap = cap * capShare / (100 * inFlight);
-    static const int envCap = [] {
-      const char* e = getenv("PCCB200_BLOCK_GRID");
-      return e ? atoi(e) : 0;
-    }();
-    if (envCap > 0)
-      cap = envCap;
-    if (cap < 8)
-      cap = 8;
-    if (blocks > cap)
-      blocks = cap;
-    if (experiment != 2) {  // (2: timing experiment without the dataflow kernel, WRONG RESULTS)
+    const int64_t blocks = block_grid(nBlocks);
+    {
       Scope sc(*this);
       k_block_warp<<<unsigned(blocks), kWarpBlockThreads, 0, stream>>>(a, ticket);
     }

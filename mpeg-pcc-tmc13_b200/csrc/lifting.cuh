@@ -39,17 +39,27 @@ struct FillU64Fn {
   PCC_HD void operator()(int64_t i) const { p[i] = v; }
 };
 
-// does any predictor in [start, start + n) reference an index >= start ?
+// flag bit 0: a predictor in [start, start + n) references an index >= start
+// (its own level of detail); bit 1: a predictor is malformed (more than three
+// neighbours, or an index outside [0, total))
 struct LodCheckFn {
   const pccb200_predictor* preds;
   int64_t start;
   int* flag;
+  int64_t total;
   PCC_HD void operator()(int64_t i) const
   {
     const pccb200_predictor& p = preds[start + i];
-    for (uint32_t j = 0; j < p.neighbor_count; j++)
-      if (int64_t(p.predictor_index[j]) >= start)
+    if (p.neighbor_count > 3) {
+      atomic_or_i32(flag, 2);
+      return;
+    }
+    for (uint32_t j = 0; j < p.neighbor_count; j++) {
+      if (int64_t(p.predictor_index[j]) >= total)
+        atomic_or_i32(flag, 2);
+      else if (int64_t(p.predictor_index[j]) >= start)
         atomic_or_i32(flag, 1);
+    }
   }
 };
 
@@ -388,12 +398,15 @@ run_quant_weights(Exec& ex, const pccb200_predictor* preds, int64_t n,
     if (s != prevEnd || e < s || e > n)
       return PCCB200_ERR_INVALID_ARG;
     prevEnd = e;
-    ex.foreach(e - s, LodCheckFn{preds, s, dFlags + l});
+    ex.foreach(e - s, LodCheckFn{preds, s, dFlags + l, n});
   }
   if (prevEnd != n)
     return PCCB200_ERR_INVALID_ARG;
   std::vector<int> flags(size_t(lodCount) + 1);
   ex.download(flags.data(), dFlags, flags.size() * sizeof(int));
+  for (int l = 0; l < lodCount; l++)
+    if (flags[l] & 2)
+      return PCCB200_ERR_INVALID_ARG;
   for (int l = lodCount - 1; l >= 0; l--) {
     int64_t s = l ? numPointsInLod[l - 1] : 0;
     int64_t e = numPointsInLod[l];
@@ -441,10 +454,12 @@ run_lift(Exec& ex, bool forward, const pccb200_predictor* preds, const uint64_t*
     int64_t s = numPointsInLod[l - 1], e = numPointsInLod[l];
     if (e < s || e > n)
       return PCCB200_ERR_INVALID_ARG;
-    ex.foreach(e - s, LodCheckFn{preds, s, dFlag});
+    ex.foreach(e - s, LodCheckFn{preds, s, dFlag, n});
   }
   int flag = 0;
   ex.download(&flag, dFlag, sizeof(int));
+  if (flag & 2)
+    return PCCB200_ERR_INVALID_ARG;
   if (flag)
     return PCCB200_ERR_UNSUPPORTED;
 

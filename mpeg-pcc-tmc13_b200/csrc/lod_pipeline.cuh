@@ -56,6 +56,14 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
       || lp.num_pred_nearest_neighbours < 1 || lp.num_pred_nearest_neighbours > 3
       || lp.lod_decimation_type < 0 || lp.lod_decimation_type > 2)
     return PCCB200_ERR_INVALID_ARG;
+  // cell shifts are 3 * (dist2 + lod + 1) bits of a 63-bit Morton code
+  if (lp.lod_decimation_type != 1
+      && (lp.dist2 < 0 || lp.dist2 + lp.num_detail_levels > 20))
+    return PCCB200_ERR_INVALID_ARG;
+  if (lp.lod_decimation_type != 0)
+    for (int l = 0; l + 1 < lp.num_detail_levels; l++)
+      if (lp.lod_sampling_period[l] < 2)
+        return PCCB200_ERR_INVALID_ARG;
   LodConfig cfg;
   cfg.numDetailLevels = lp.num_detail_levels;
   cfg.decimation = lp.lod_decimation_type;
@@ -129,8 +137,7 @@ lod_run(Exec& ex, const pccb200_lod_params& lp, const int32_t* xyz, int N,
       ex.foreach(nInput, SubsamplePeriodicFn{input, retained, queries, period});
     } else {
       // cells / octree nodes: runs of equal (code >> shift)
-      const int shift = cfg.decimation == 0 ? 3 * (cfg.dist2 + lod + 1)
-                                            : 3 * (cfg.dist2 + lod + 1);
+      const int shift = 3 * (cfg.dist2 + lod + 1);
       ex.compact(nInput, CellHead{code, input, shift}, CellEmit{cellFirst}, dCount);
       int nCells = 0;
       ex.download(&nCells, dCount, sizeof(int));

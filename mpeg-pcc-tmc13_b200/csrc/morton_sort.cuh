@@ -223,6 +223,47 @@ grid_for(int64_t n, int numSMs)
   return unsigned(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Stable LSD radix sort of (int64 key, int32 value) pairs on the low
+// 8 * passes key bits.  The pairs ping-pong between (keysA, valsA) and
+// (keysB, valsB); *keysRes / *valsRes say where the result landed.
+inline void
+device_radix_sort_pairs(DeviceExec& ex, int64_t* keysA, int32_t* valsA, int64_t* keysB,
+                        int32_t* valsB, int64_t n, int passes, int64_t** keysRes,
+                        int32_t** valsRes)
+{
+  cudaStream_t st = ex.stream;
+  const int numTiles = int((n + kSortTile - 1) / kSortTile);
+  const int64_t histLen = int64_t(256) * numTiles;
+  int* hist = ex.alloc<int>(histLen);
+  const int scanTiles = int((histLen + kTile - 1) / kTile);
+  int* tileSums = ex.alloc<int>(scanTiles);
+
+  int64_t* kin = keysA;
+  int32_t* vin = valsA;
+  int64_t* kout = keysB;
+  int32_t* vout = valsB;
+  for (int p = 0; p < passes; p++) {
+    const int shift = 8 * p;
+    DeviceExec::Scope sc(ex);
+    k_radix_hist<<<numTiles, kSortThreads, 0, st>>>(kin, n, shift, numTiles, hist);
+    k_scan_sum<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tileSums, scanTiles, nullptr);
+    k_scan_apply<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
+    k_radix_scatter<<<numTiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift,
+                                                       numTiles, hist);
+    g_launchCount += 5;
+    int64_t* tk = kin;
+    kin = kout;
+    kout = tk;
+    int32_t* tv = vin;
+    vin = vout;
+    vout = tv;
+  }
+  PCC_CUDA_CHECK(cudaGetLastError());
+  *keysRes = kin;
+  *valsRes = vin;
+}
+
 // Sorts n points; keysOut / orderOut are device buffers of n entries.
 // Uses the executor's arena for scratch.  One synchronising read-back (the OR
 // of all keys) decides the number of passes.
@@ -253,38 +294,13 @@ device_morton_sort(DeviceExec& ex, const int32_t* dXyz, int64_t n, int64_t* keys
   if (passes == 0)
     return;  // all keys zero: already sorted, order = identity
 
-  const int numTiles = int((n + kSortTile - 1) / kSortTile);
-  const int64_t histLen = int64_t(256) * numTiles;
-  int* hist = ex.alloc<int>(histLen);
-  const int scanTiles = int((histLen + kTile - 1) / kTile);
-  int* tileSums = ex.alloc<int>(scanTiles);
-
-  int64_t* kin = keysOut;
-  int32_t* vin = orderOut;
-  int64_t* kout = keysTmp;
-  int32_t* vout = valsTmp;
-  for (int p = 0; p < passes; p++) {
-    const int shift = 8 * p;
-    DeviceExec::Scope sc(ex);
-    k_radix_hist<<<numTiles, kSortThreads, 0, st>>>(kin, n, shift, numTiles, hist);
-    k_scan_sum<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
-    k_scan_tiles<<<1, 1024, 0, st>>>(tileSums, scanTiles, nullptr);
-    k_scan_apply<<<scanTiles, kTileThreads, 0, st>>>(hist, histLen, tileSums);
-    k_radix_scatter<<<numTiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift,
-                                                       numTiles, hist);
-    g_launchCount += 5;
-    int64_t* tk = kin;
-    kin = kout;
-    kout = tk;
-    int32_t* tv = vin;
-    vin = vout;
-    vout = tv;
-  }
-  PCC_CUDA_CHECK(cudaGetLastError());
-  if (kin != keysOut) {
-    PCC_CUDA_CHECK(cudaMemcpyAsync(keysOut, kin, n * sizeof(int64_t),
+  int64_t* kres = nullptr;
+  int32_t* vres = nullptr;
+  device_radix_sort_pairs(ex, keysOut, orderOut, keysTmp, valsTmp, n, passes, &kres, &vres);
+  if (kres != keysOut) {
+    PCC_CUDA_CHECK(cudaMemcpyAsync(keysOut, kres, n * sizeof(int64_t),
                                    cudaMemcpyDeviceToDevice, st));
-    PCC_CUDA_CHECK(cudaMemcpyAsync(orderOut, vin, n * sizeof(int32_t),
+    PCC_CUDA_CHECK(cudaMemcpyAsync(orderOut, vres, n * sizeof(int32_t),
                                    cudaMemcpyDeviceToDevice, st));
   }
 }

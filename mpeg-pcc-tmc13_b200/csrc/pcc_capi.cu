@@ -23,6 +23,7 @@
 #include "morton_sort.cuh"
 #include "pcc_attr_b200.h"
 #include "raht_pipeline.cuh"
+#include "raht_wave.cuh"
 #include "spherical.cuh"
 #include "symbols.cuh"
 #include "dist2.cuh"
@@ -44,6 +45,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   Arena arena;
   unsigned long long* ticket = nullptr;
+  cudaEvent_t tail = nullptr;  // "everything queued so far" marker (pccb200_time_end)
   Profiler prof;
   bool busy = false;
 };
@@ -87,9 +89,8 @@ ensure_ready(Context& c)
 {
   if (c.ready)
     return PCCB200_OK;
-  // one hardware queue per lane (effective only if this process has not
-  // created its CUDA context yet; bench.py sets it itself before torch does)
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  // (one hardware queue per lane needs CUDA_DEVICE_MAX_CONNECTIONS=32 in the
+  // application's environment before its CUDA context exists: see the header)
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0) {
@@ -124,6 +125,9 @@ make_lane(Context& c, Lane& l)
   e = cudaMalloc(&l.ticket, 256);
   if (e != cudaSuccess)
     return fail(PCCB200_ERR_NOMEM, cudaGetErrorString(e));
+  e = cudaEventCreateWithFlags(&l.tail, cudaEventDisableTiming);
+  if (e != cudaSuccess)
+    return fail(PCCB200_ERR_CUDA, cudaGetErrorString(e));
   return PCCB200_OK;
 }
 
@@ -134,6 +138,8 @@ destroy_lanes(Context& c)
     cudaStreamSynchronize(l->stream);
     l->arena.release();
     cudaFree(l->ticket);
+    if (l->tail)
+      cudaEventDestroy(l->tail);
     cudaStreamDestroy(l->stream);
   }
   c.lanes.clear();
@@ -196,7 +202,7 @@ with_device(Body body)
   int rc;
   try {
     PCC_CUDA_CHECK(cudaSetDevice(c.device));
-    lane->arena.reset();
+    lane->arena.reset(c.active.load() == 1);
     DeviceExec ex;
     ex.stream = lane->stream;
     ex.arena = &lane->arena;
@@ -213,7 +219,15 @@ with_device(Body body)
     cudaGetLastError();
     rc = fail(e.code == cudaErrorMemoryAllocation ? PCCB200_ERR_NOMEM : PCCB200_ERR_CUDA,
               std::string(e.what) + ": " + cudaGetErrorString(e.code));
+  } catch (const std::bad_alloc&) {
+    rc = fail(PCCB200_ERR_NOMEM, "host allocation failed");
+  } catch (const std::exception& e) {
+    rc = fail(PCCB200_ERR_CUDA, std::string("internal error: ") + e.what());
+  } catch (...) {
+    rc = fail(PCCB200_ERR_CUDA, "internal error");
   }
+  if (rc != PCCB200_OK)  // nothing of a failed call may still be running on the lane
+    cudaStreamSynchronize(lane->stream);
   {
     std::lock_guard<std::mutex> lock(c.mu);
     for (int i = 0; i < PCCB200_NUM_PHASES; i++) {
@@ -251,7 +265,12 @@ parallel_for(int n, int maxThreads, Fn fn)
       int i = next.fetch_add(1);
       if (i >= n)
         return;
-      int rc = fn(i);
+      int rc;
+      try {
+        rc = fn(i);
+      } catch (...) {  // a worker thread must not let anything escape
+        rc = fail(PCCB200_ERR_CUDA, "internal error in a slice worker");
+      }
       if (rc) {
         int expected = 0;
         if (status.compare_exchange_strong(expected, rc)) {
@@ -619,11 +638,8 @@ pccb200_time_end(double* ms_out)
     return fail(PCCB200_ERR_INVALID_ARG, "pccb200_time_begin not called");
   cudaSetDevice(c.device);
   for (auto& l : c.lanes) {
-    cudaEvent_t e;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaEventRecord(e, l->stream);
-    cudaStreamWaitEvent(c.timeStream, e, 0);
-    cudaEventDestroy(e);
+    cudaEventRecord(l->tail, l->stream);
+    cudaStreamWaitEvent(c.timeStream, l->tail, 0);
   }
   cudaEventRecord(c.timeEnd, c.timeStream);
   cudaEventSynchronize(c.timeEnd);

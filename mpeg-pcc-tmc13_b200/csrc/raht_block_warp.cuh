@@ -38,12 +38,15 @@ struct WarpBlockArgs {
   int32_t* geom;            // kGeomStride ints per worklist entry (see k_block_geom)
   const int* count;         // number of worklist entries (device memory)
   int64_t ab11a, ab11b;     // RahtKernel(1, 1), the commonest butterfly
-  int experiment;           // timing experiments only (PCCB200_EXPERIMENT), 0 in production
   const struct TzRegion* regions;  // zero-run words/lists of every stage so far
   int stageIdx;                    // index of this stage in regions (0 = root)
   int* words;                      // regions[stageIdx].words / .lists (kernel parameters:
   unsigned long long* lists;       //   no load on the critical path)
   int pollNs;                      // sleep between polls of a value still being produced
+  // wavefront schedule (raht_wave.cuh): ticket i runs the block of row
+  // order[i] (worklist rank + orderBase), rows sorted by dependency level
+  const int32_t* order;
+  int orderBase;
 };
 
 // Zero-run bookkeeping of one stage, indexed by worklist rank t:
@@ -61,8 +64,6 @@ constexpr int kWarpBlockThreads = 256;
 #ifndef PCCB200_BLOCK_MIN_CTAS
 #  define PCCB200_BLOCK_MIN_CTAS 3  // resident CTAs per SM the block kernel is compiled for
 #endif
-constexpr int kWarpBlockChunk = 1;  // blocks claimed per ticket (consecutive blocks in one
-                                    // warp would serialise the zero-run look-back chain)
 constexpr int kGeomStride = 20;     // ints per block: 19 neighbour indices + count
 
 __device__ __forceinline__ int64_t
@@ -297,7 +298,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   uint32_t validMask = 0;             // neighbours that contribute
   if (a.predInLvl) {
     const int g = lane < kGeomStride ? a.geom[size_t(t) * kGeomStride + lane] : -1;
-    const int count = __shfl_sync(0xffffffffu, g, 19);
+    const int count = __shfl_sync(0xffffffffu, g, 19) & 0xff;
     const int nq = lane < 19 ? g : -1;
     enablePred = count >= cfg.thr1 && __shfl_sync(0xffffffffu, g, 0) >= 0;
     if (enablePred) {
@@ -492,13 +493,13 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
           }
         }
       }
-      // wait for all of them at once
+      // wait for all of them at once (the loop is uniform over the warp)
       for (;;) {
         bool pending = false;
 #pragma unroll
         for (int u = 0; u < 4; u++)
           pending |= ad[u] && v[u] == kRecNotReady;
-        if (!pending)
+        if (!__any_sync(0xffffffffu, pending))
           break;
         __nanosleep(a.pollNs);
 #pragma unroll
@@ -618,7 +619,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         if ((softM >> m) & 1) {
           const int th = thr_decode(int((codes >> (6 * m)) & 63));
           if (linked)
-            f = a.experiment == 1 ? false : tz_run_at_least(a, t, th - z);
+            f = tz_run_at_least(a, t, th - z);
           else
             f = tl >= th;
         }
@@ -702,15 +703,31 @@ k_block_geom(const WarpBlockArgs a)
       pidx = find_parent_neighbour(P, p, plevel, cur, base, lane, cfg.searchRange);
     count = __popc(__ballot_sync(0xffffffffu, pidx >= 0));
   }
+  // same-stage dependencies: neighbour i >= 7 precedes the block, transforms
+  // (a single-child block is passed through before the stage starts) and one
+  // of its children is read by the sub-node prediction (RAHT.cpp:370-415)
+  bool dep = false;
+  if (cfg.subnode && count >= cfg.thr1 && lane >= 7 && lane < 19 && pidx >= 0 && pidx < p) {
+    const int ii = lane - 7;
+    const int sh = occu_shift(ii);
+    const uint32_t nocc = P.occ[pidx];
+    const uint32_t cmask = (ii < 9 ? (nocc >> sh) : (nocc << sh)) & uint32_t(neigh_mask(lane)) & occ & 0xffu;
+    dep = cmask != 0 && P.first[pidx + 1] - P.first[pidx] >= 2;
+  }
+  const uint32_t depMask = (__ballot_sync(0xffffffffu, dep) >> 7) & 0xfffu;
   if (lane < 19)
     a.geom[size_t(t) * kGeomStride + lane] = pidx;
   else if (lane == 19)
-    a.geom[size_t(t) * kGeomStride + 19] = count;
+    a.geom[size_t(t) * kGeomStride + 19] = count | int(depMask << 8);
   // the count is inherited by the children's blocks at the next stage
   if (lane < 8 && ((occ >> lane) & 1))
     S.nn[P.first[p] + __popc(occ & ((1u << lane) - 1))] = count;
 }
 
+// Tickets are claimed in ascending order; ticket i runs worklist entry i
+// (Morton = coding order) or, with a wavefront schedule, entry order[i].  Either
+// way everything a block may wait for has a lower ticket, i.e. is owned by a
+// running warp.
 __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
@@ -719,19 +736,27 @@ k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0)
-      base = atomicAdd(ticket, (unsigned long long)kWarpBlockChunk);
+      base = atomicAdd(ticket, 1ull);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= (unsigned long long)n)
       return;
-#pragma unroll 1
-    for (int i = 0; i < kWarpBlockChunk; i++) {
-      const int t = int(base) + i;
-      if (t >= n)
-        break;
-      const int p = a.worklist ? a.worklist[t] : 0;
-      warp_block(a, p, t, lane);
-    }
+    const int t = a.order ? a.order[base] - a.orderBase : int(base);
+    const int p = a.worklist ? a.worklist[t] : 0;
+    warp_block(a, p, t, lane);
   }
+}
+
+__device__ __forceinline__ int
+ld_relaxed_i32(const int* p)
+{
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void
+st_relaxed_i32(int* p, int v)
+{
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 }  // namespace pccb200

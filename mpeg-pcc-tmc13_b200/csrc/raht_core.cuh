@@ -900,17 +900,19 @@ struct PrepFn {
   int predInLvl;
   int* tzByBlock;  // block-indexed look-back words (or null): a single-child
                    // block publishes "transparent, 0 coefficients"
+  int mode = 0;    // 0: everything; 1: the value-free part only (qps, neighbour
+                   // counts); 2: the values only (pass-through)
   PCC_HD void operator()(int64_t pb) const
   {
     const int p = int(pb);
     const int c0 = P.first[p], c1 = P.first[p + 1];
-    if (cfg.hasQp)
+    if (cfg.hasQp && mode != 2)
       descend_qps(S, c0, c1, &P.qpDown[2 * p]);
     if (c1 - c0 != 1)
       return;
     const int c = c0;
     const int A = cfg.A;
-    if (predInLvl) {
+    if (predInLvl && mode != 2) {
       int count = 0;
       if (cfg.ext) {
         count = 19;
@@ -926,6 +928,8 @@ struct PrepFn {
       }
       S.nn[c] = count;
     }
+    if (mode == 1)
+      return;
     const int wgt = S.weight[c];
     for (int k = 0; k < A; k++) {
       int64_t v = P.recUs[size_t(p) * A + k];

@@ -32,6 +32,14 @@
 
 namespace pccb200 {
 
+// An executor may provide its own schedule of the whole descent (specialised
+// for the CUDA executor in raht_wave.cuh); the generic one below walks the
+// stages through Exec::block_stage.
+template<class Exec>
+struct WaveDescent {
+  static constexpr bool available = false;
+};
+
 struct StagePlan {
   int level;
   int n;
@@ -223,8 +231,17 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
       ex.upload(tz + tzOff[stages.size() - 1], &init, sizeof(int));
     }
 
+    bool descended = false;
+    if constexpr (WaveDescent<Exec>::available) {
+      if (WaveDescent<Exec>::enabled(cfg)) {
+        qpLayer = WaveDescent<Exec>::run(ex, cfg, qt, stages, coef, coefStride, qs.num_layers,
+                                         tz, tzOff);
+        descended = true;
+      }
+    }
+
     int acLayer = -1;
-    for (int si = int(stages.size()) - 1; si >= 0; si--) {
+    for (int si = int(stages.size()) - 1; si >= 0 && !descended; si--) {
       qpLayer = qpLayer + 1 < qs.num_layers ? qpLayer + 1 : qs.num_layers - 1;
       acLayer++;
       BlockFn fn;

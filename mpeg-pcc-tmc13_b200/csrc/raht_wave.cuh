@@ -1,0 +1,323 @@
+// raht_wave.cuh — wavefront schedule of the top-down block transform
+// (device only).
+//
+// Sub-node prediction (tmc3/RAHT.cpp:370-415) makes a block wait for the
+// earlier neighbour blocks whose children it reads.  Claimed in Morton order,
+// the members of a chain are all claimed at about the same time and their
+// warps sit on them until the chain has been worked off.  Without the
+// encoder's RDOQ (decoder; integer Haar) those are the only dependencies
+// inside a stage, they follow from geometry alone, and the blocks can be
+// claimed in dependency-level ("wavefront") order instead, so that a block is
+// normally ready when a warp takes it.  With RDOQ the zero-run look-back
+// (RAHT.cpp:1154,1576-1670) follows coding order and may reach arbitrarily far
+// back: coding order stays the ticket order there (a wavefront order with
+// bounded waits and restarts was measured: 6 to 500 times slower).
+// The schedule, computed before any attribute value is read:
+//
+//   1. geometry of every stage (top-down, fully parallel kernels): qp
+//      descent + neighbour counts of single-child blocks (PrepFn, mode 1),
+//      worklist of the transforming blocks, the 18 neighbour searches and the
+//      same-stage dependency mask of each (k_block_geom);
+//   2. (no RDOQ) dependency level of every block, all stages in one launch
+//      (k_block_levels): 1 + max level of the earlier neighbour blocks whose
+//      children it reads;
+//   3. (no RDOQ) one stable radix sort of all rows by (stage, level);
+//   4. the stages, coarse to fine: reconstruction slots armed, single-child
+//      blocks passed through (PrepFn, mode 2), k_block_warp over the worklist
+//      in schedule order.
+//
+// Steps 1-3 read no attribute value: they are the same for every attribute
+// coded on the same positions.
+#pragma once
+
+#include "morton_sort.cuh"
+#include "raht_pipeline.cuh"
+
+namespace pccb200 {
+
+constexpr int kMaxWaveSegs = 24;   // descent steps below the root (<= 21)
+
+struct LevelArgs {
+  int numSeg;                   // segments 1..numSeg
+  int rowOff[kMaxWaveSegs + 2]; // rowOff[d]; rowOff[numSeg + 1] = number of rows
+  const int* cnt;               // cnt[d]: transforming blocks of segment d
+  const int32_t* wl;            // row -> block index (first cnt[d] rows of a segment)
+  const int32_t* geom;          // kGeomStride ints per row
+  int* lv;                      // per (segment, block index): dependency level, 0 = not known yet
+  int64_t* key;                 // per row: segment << 16 | level (0xffff: unused row)
+  int32_t* val;                 // per row: the row itself
+};
+
+// qp descent of the root block (the root block's kernel repeats it)
+struct RootQpFn {
+  Stage S;
+  PCC_HD void operator()(int64_t) const { descend_qps(S, 0, S.n, nullptr); }
+};
+
+struct FillI32 {
+  int32_t* p;
+  int32_t v;
+  PCC_HD void operator()(int64_t i) const { p[i] = v; }
+};
+
+// One thread per row, 32 consecutive rows per ticket, rows in coding order:
+// everything a row waits for has a lower row number, hence a ticket that has
+// been claimed.  The loop is uniform over the warp (a lane never spins while
+// another lane of its warp could be the one it is waiting for).
+__global__ void __launch_bounds__(256)
+k_block_levels(const LevelArgs a, unsigned long long* ticket)
+{
+  const int lane = threadIdx.x & 31;
+  const long long numRows = a.rowOff[a.numSeg + 1];
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)numRows)
+      return;
+    const long long row = (long long)base + lane;
+    int d = 1, off = 0, t = 0, p = 0;
+    bool active = false;
+    if (row < numRows) {
+      while (d < a.numSeg && row >= a.rowOff[d + 1])
+        d++;
+      off = a.rowOff[d];
+      t = int(row) - off;
+      active = t < a.cnt[d];
+      a.val[row] = int32_t(row);
+      if (!active)
+        a.key[row] = (int64_t(d) << 16) | 0xffff;
+    }
+    uint32_t depMask = 0;
+    int q[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      q[i] = 0;
+    if (active) {
+      p = a.wl[row];
+      const int32_t* g = a.geom + size_t(row) * kGeomStride;
+      depMask = (uint32_t(g[19]) >> 8) & 0xfffu;
+#pragma unroll
+      for (int i = 0; i < 12; i++)
+        if ((depMask >> i) & 1)
+          q[i] = g[7 + i];
+    }
+    bool done = !active;
+    while (__any_sync(0xffffffffu, !done)) {
+      bool progress = false;
+      if (!done) {
+        int m = 0;
+        bool ready = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+          if ((depMask >> i) & 1) {
+            const int v = ld_relaxed_i32(&a.lv[off + q[i]]);
+            if (!v)
+              ready = false;
+            else
+              m = v > m ? v : m;
+          }
+        if (ready) {
+          m++;
+          st_relaxed_i32(&a.lv[off + p], m);
+          a.key[row] = (int64_t(d) << 16) | (m < 0xfffe ? m : 0xfffe);
+          done = true;
+          progress = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, progress))
+        __nanosleep(40);
+    }
+  }
+}
+
+template<>
+struct WaveDescent<DeviceExec> {
+  static constexpr bool available = true;
+
+  static bool enabled(const RahtConfig& cfg)
+  {
+    static const int mode = [] {
+      const char* e = getenv("PCCB200_BLOCK_KERNEL");
+      if (!e)
+        return 0;
+      return !strcmp(e, "thread") ? 1 : !strcmp(e, "warp") ? 2 : 0;
+    }();
+    if (mode)
+      return false;
+    // AC-coefficient qp offsets in the encoder keep the exact-counter protocol
+    // of the thread-per-block body (see DeviceExec::block_stage)
+    if (cfg.isEncoder && !cfg.haar && cfg.numAcLayers > 0)
+      return false;
+    return true;
+  }
+
+  // stages[0] = leaves ... stages.back() = children of the root block.
+  // tz / tzOff: zero-run words as laid out by raht_run.  Returns the qp layer
+  // of the last stage (for the duplicate tail).
+  static int run(DeviceExec& ex, const RahtConfig& cfg, const QpTables* qt,
+                 const std::vector<Stage>& stages, int32_t* coef, int64_t coefStride,
+                 int numLayers, int* tz, const std::vector<int64_t>& tzOff)
+  {
+    const int top = int(stages.size()) - 1;
+    const int A = cfg.A;
+    const bool rdoq = cfg.isEncoder && !cfg.haar;
+    static const int pollNs = [] {
+      const char* e = getenv("PCCB200_POLL_NS");
+      return e ? atoi(e) : 32;
+    }();
+    static const bool mortonOrder = [] {  // A/B: coding order everywhere
+      const char* e = getenv("PCCB200_WAVE_ORDER");
+      return e && !strcmp(e, "morton");
+    }();
+    const bool wave = cfg.predictionEnabled && cfg.subnode && !rdoq && !mortonOrder;
+
+    //-- row space: one segment per descent step below the root
+    LevelArgs la = {};
+    la.numSeg = top;
+    int64_t numRows = 0;
+    for (int d = 1; d <= top; d++) {
+      la.rowOff[d] = int(numRows);
+      numRows += stages[top - d + 1].n;
+    }
+    la.rowOff[top + 1] = int(numRows);
+    la.rowOff[0] = 0;
+
+    int32_t* wl = ex.alloc<int32_t>(size_t(numRows));
+    int32_t* geom = cfg.predictionEnabled ? ex.alloc<int32_t>(size_t(numRows) * kGeomStride) : nullptr;
+    int* cnt = ex.alloc<int>(top + 2);
+    // zeroed in one go: the ticket word of every step, the levels
+    const size_t zInts = size_t(top + 2) * 2 + (wave ? size_t(numRows) : 0);
+    int* zero = ex.alloc<int>(zInts);
+    ex.zero(zero, zInts * sizeof(int));
+    unsigned long long* tickets = reinterpret_cast<unsigned long long*>(zero);
+    int* lv = zero + size_t(top + 2) * 2;
+
+    //-- 1. geometry, top-down
+    ex.phase(kPhaseGeom);
+    ex.foreach(stages[top].n, FillI32{stages[top].nn, 19});
+    if (cfg.hasQp)
+      ex.foreach(1, RootQpFn{stages[top]});
+    int64_t abA, abB;
+    raht_ab(1, 1, abA, abB);
+    std::vector<WarpBlockArgs> args(top + 1);
+    for (int d = 1; d <= top; d++) {
+      const int si = top - d;
+      const Stage& S = stages[si];
+      const Stage& P = stages[si + 1];
+      const int nBlocks = P.n;
+      PrepFn prep{cfg, S, P, cfg.predictionEnabled, nullptr, 1};
+      if (cfg.hasQp || cfg.predictionEnabled)
+        ex.foreach(nBlocks, prep);
+      ex.compact(nBlocks, MultiChildPred{P.first}, WorklistEmit{wl + la.rowOff[d]}, cnt + d);
+      WarpBlockArgs& a = args[d];
+      a = WarpBlockArgs{};
+      a.cfg = cfg;
+      a.qt = qt;
+      a.S = S;
+      a.P = P;
+      a.coef = coef;
+      a.coefStride = coefStride;
+      a.coefBase = P.n;
+      a.predInLvl = cfg.predictionEnabled;
+      a.worklist = wl + la.rowOff[d];
+      a.geom = geom ? geom + size_t(la.rowOff[d]) * kGeomStride : nullptr;
+      a.count = cnt + d;
+      a.ab11a = abA;
+      a.ab11b = abB;
+      a.pollNs = pollNs;
+      if (cfg.predictionEnabled) {
+        DeviceExec::Scope sc(ex);
+        k_block_geom<<<unsigned((int64_t(nBlocks) * 32 + 255) / 256), 256, 0, ex.stream>>>(a);
+        g_launchCount++;
+      }
+    }
+
+    //-- 2 + 3. dependency levels, wavefront order
+    const int32_t* order = nullptr;
+    if (wave && numRows > 0) {
+      ex.phase(kPhaseOrder);
+      int64_t* keyA = ex.alloc<int64_t>(size_t(numRows));
+      int64_t* keyB = ex.alloc<int64_t>(size_t(numRows));
+      int32_t* valA = ex.alloc<int32_t>(size_t(numRows));
+      int32_t* valB = ex.alloc<int32_t>(size_t(numRows));
+      la.cnt = cnt;
+      la.wl = wl;
+      la.geom = geom;
+      la.lv = lv;
+      la.key = keyA;
+      la.val = valA;
+      {
+        DeviceExec::Scope sc(ex);
+        int64_t blocks = (numRows + 255) / 256;
+        const int64_t cap = int64_t(ex.numSMs) * 8;
+        k_block_levels<<<unsigned(blocks > cap ? cap : blocks), 256, 0, ex.stream>>>(la, tickets);
+        g_launchCount++;
+      }
+      int64_t* kres;
+      int32_t* vres;
+      device_radix_sort_pairs(ex, keyA, valA, keyB, valB, numRows, 3, &kres, &vres);
+      order = vres;
+    }
+
+    //-- 4. the stages
+    ex.phase(kPhaseBlock);
+    int qpLayer = 0;
+    int acLayer = -1;
+    for (int d = 0; d <= top; d++) {
+      const int si = top - d;
+      qpLayer = qpLayer + 1 < numLayers ? qpLayer + 1 : numLayers - 1;
+      acLayer++;
+      const Stage& S = stages[si];
+      ex.fill(S.rec, 0x80, size_t(S.n) * A * sizeof(int64_t));
+      if (d == 0) {
+        // the root block: the kernel of the Morton-order path, one block
+        BlockFn fn;
+        fn.cfg = cfg;
+        fn.qt = qt;
+        fn.S = S;
+        fn.P = Stage{};
+        fn.P.n = 0;
+        fn.coef = coef;
+        fn.coefStride = coefStride;
+        fn.coefBase = 0;
+        fn.qpLayer = qpLayer;
+        fn.acLayer = acLayer;
+        fn.predInLvl = 0;
+        fn.useFlags = 1;
+        fn.tz = tz ? tz + tzOff[si] : nullptr;
+        ex.block_stage(fn, 1, nullptr);
+        continue;
+      }
+      const Stage& P = stages[si + 1];
+      const int nBlocks = P.n;
+      ex.foreach(nBlocks, PrepFn{cfg, S, P, cfg.predictionEnabled, nullptr, 2});
+      WarpBlockArgs& a = args[d];
+      a.qpLayer = qpLayer;
+      a.acLayer = acLayer;
+      TzRegion hr;
+      hr.words = tz ? tz + tzOff[si] : nullptr;
+      hr.lists = tz ? ex.alloc<int>((size_t(nBlocks) + 1) * 2) : nullptr;
+      hr.count = cnt + d;
+      a.stageIdx = ex.numRegions;
+      ex.upload(ex.dRegions + ex.numRegions, &hr, sizeof(TzRegion));
+      ex.numRegions++;
+      a.regions = ex.dRegions;
+      a.words = hr.words;
+      a.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+      a.order = order ? order + la.rowOff[d] : nullptr;
+      a.orderBase = la.rowOff[d];
+      {
+        DeviceExec::Scope sc(ex);
+        k_block_warp<<<unsigned(ex.block_grid(nBlocks)), kWarpBlockThreads, 0, ex.stream>>>(
+          a, tickets + d);
+        g_launchCount++;
+      }
+      PCC_CUDA_CHECK(cudaGetLastError());
+    }
+    return qpLayer;
+  }
+};
+
+}  // namespace pccb200

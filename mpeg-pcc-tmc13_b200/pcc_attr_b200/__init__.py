@@ -8,6 +8,10 @@ import os
 
 import numpy as np
 
+# one hardware queue per library lane (see the header: the application sets it,
+# before its CUDA context exists; this binding is the application here)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libpcc_attr_b200.so")
 
@@ -87,8 +91,9 @@ EXPORTS = [
     "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols", "pccb200_estimate_dist2",
     "pccb200_quant_weights_fixed", "pccb200_quant_weights_scalable",
 ]
-NUM_PHASES = 6
-PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting"]
+NUM_PHASES = 8
+PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting",
+               "block_geometry", "block_schedule"]
 
 
 class PccB200Error(RuntimeError):

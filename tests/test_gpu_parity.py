@@ -170,6 +170,31 @@ def test_full_size_properties(b200):
     assert np.abs(rec - attrs).mean() < 16  # lossy but sane at qp 34
 
 
+@pytest.mark.parametrize("tex", [0, 16, 40])
+def test_full_size_vs_oracle(b200, tex):
+    """BASELINE config-2 size against the oracle, bit-exact: 1M-point LiDAR
+    cloud, RGB and reflectance, smooth attributes (zero runs thousands of
+    coefficients long) and textured ones (most positions quantise to 1 or 2:
+    every block asks for the zero-run state of its predecessors)."""
+    from pcc_attr_b200.synth import texture
+
+    xyz, rgb = cloud_lidar(1000000, seed=2)
+    refl = ((rgb[:, :1] * 3 + rgb[:, 1:2]) // 4).astype(np.int32)
+    if tex:
+        rgb, refl = texture(rgb, tex, 11), texture(refl, tex + 8, 12)
+    params, qpset = make_params(search_range=2500), make_qpset(qp=34)
+    p, q = _as(b200, params, qpset)
+    for attrs in (rgb, refl):
+        mort, a_s, order = sort_cloud(xyz, attrs)
+        orec, ocoef = oracle_raht(1, params, qpset, mort, a_s)
+        exp = np.empty_like(orec)
+        exp[order] = np.clip(orec, 0, 255)
+        rec, coef = b200.attr_raht_encode(p, q, xyz, attrs)
+        assert np.array_equal(coef, ocoef), (tex, attrs.shape)
+        assert np.array_equal(rec, exp), (tex, attrs.shape)
+        assert np.array_equal(b200.attr_raht_decode(p, q, xyz, coef), exp)
+
+
 @pytest.mark.parametrize("a", [1, 3])
 def test_lifting_vs_oracle(b200, a):
     """quantisation weights and forward / inverse lifting (64-bit atomics per
