@@ -63,15 +63,23 @@ METRIC = "attribute-transform Mpoints/s (RAHT forward: Morton sort + transform, 
 ALG_BYTES_PER_POINT = (16 + 12 * 3) + (16 + 12 * 1)  # 52 (RGB) + 28 (reflectance)
 
 
-def workload_config():
+FRAMES_PER_STEP = 16
+
+
+def workload_config(frames=FRAMES_PER_STEP):
+    """identical for both arms (the driver compares the dicts)"""
     return {
         "workload": "configs[1]: octree-raht lossy-attrs, ~1M-point synthetic LiDAR ring cloud "
                     "(Ford_01-shaped), RGB + reflectance, single slice",
         "points_per_frame": N_POINTS,
         "attributes": "RGB (A=3) + reflectance (A=1), 8-bit",
+        "attribute_model": f"smooth field + per-point texture of +-{TEXTURE_RGB} (RGB) / "
+                           f"+-{TEXTURE_REFL} (reflectance): about a quarter of the RGB and a "
+                           f"sixth of the reflectance coefficient positions quantise to 1 or 2 "
+                           f"at qp {QP} (the zero-run / RDOQ chain is exercised on every block)",
         "qp": QP,
         "raht": "prediction + sub-node prediction, rahtExtension, RDOQ, search range 2500",
-        "frames_per_step_per_gpu": 16,
+        "frames_per_step_per_gpu": frames,
         "parallelism": "frames shard across GPUs, no data-path collective",
         "l2": "512 MiB written between steps (excluded from timing) to flush L2",
     }
@@ -270,7 +278,21 @@ def host_cpu_model():
     return "unknown"
 
 
+def coefficient_histogram(coefs):
+    """zero / soft (sum |q| in {1,2}) / hard positions of a list of [A, N] planes"""
+    out = {}
+    for name, c in coefs:
+        sm = np.abs(c.astype(np.int64)).sum(axis=0)
+        n = float(sm.size)
+        out[name] = {"zero": float((sm == 0).sum() / n), "soft": float(((sm > 0) & (sm < 3)).sum() / n),
+                     "hard": float((sm >= 3).sum() / n)}
+    return out
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle/_ref: the
+    unmodified sources compiled here; else the oracle port) on the host's
+    physical cores: each step = one frame of the workload per thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -280,14 +302,14 @@ def run_reference_arm(args):
     run, kind = load_cpu_impl()
     params = tl.make_params(search_range=SEARCH_RANGE)
     qpset = tl.make_qpset(qp=QP, chroma_offset=CHROMA_OFFSET)
-    frame = make_frame(2)
-    cores = min(os.cpu_count() or 1, 64)
+    cores = physical_cores()
     if kind == "port":
         cores = 1  # the oracle port is driven through numpy here: one thread
+    frames = [make_frame(sd) for sd in frame_seeds(0, min(4, cores))]
 
     def one_step():
-        ts = [threading.Thread(target=cpu_frame_seconds, args=(run, params, qpset, frame))
-              for _ in range(cores)]
+        ts = [threading.Thread(target=cpu_frame_seconds, args=(run, params, qpset, frames[i % len(frames)]))
+              for i in range(cores)]
         t0 = time.perf_counter()
         for t in ts:
             t.start()
@@ -295,24 +317,26 @@ def run_reference_arm(args):
             t.join()
         return time.perf_counter() - t0
 
+    one_core = cpu_frame_seconds(run, params, qpset, frames[0])
     for _ in range(args.warmup):
         one_step()
     total = 0.0
     for _ in range(args.steps):
         total += one_step()
-    n = frame[0].shape[0]
+    n = frames[0][0].shape[0]
     value = cores * n * args.steps / total / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": workload_config(),
+        "config": workload_config(args.frames),
         "cpu_baseline": {
             "value": value, "unit": "Mpoints/s", "cores": cores, "kind": kind,
-            "sample": f"each step: {cores} independent copies of the 1 frame workload "
-                      f"({n} points, RGB + reflectance), one per host thread "
-                      f"(the reference itself is single-threaded); host: {host_cpu_model()}"},
+            "value_one_core": n / one_core / 1e6,
+            "sample": f"each step: one frame of the workload ({n} points, RGB + reflectance) per "
+                      f"host thread, {cores} threads = the physical cores ({len(frames)} distinct "
+                      f"frames; the reference itself is single-threaded); host: {host_cpu_model()}"},
         "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -364,6 +388,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(torch, local)
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -379,40 +404,42 @@ def run_ours(args):
         raw = broadcast_pods(bytes(params) + bytes(qpset), dist, dev)
         params = pb.RahtParams.from_buffer_copy(raw[:C.sizeof(pb.RahtParams)])
         qpset = pb.QpSet.from_buffer_copy(raw[C.sizeof(pb.RahtParams):])
+    qpsets = [qpset, qpset]
 
     F = args.frames
     frames = [make_frame(sd) for sd in frame_seeds(rank, F)]
     n = frames[0][0].shape[0]
-    pool = ThreadPoolExecutor(max_workers=2 * F)
+    pool = ThreadPoolExecutor(max_workers=F)  # one host thread per call in flight
 
     # ---- device-resident inputs -------------------------------------------
-    dv = []
-    for xyz, rgb, refl in frames:
-        d = {"xyz": torch.from_numpy(xyz).to(dev), "rgb0": torch.from_numpy(rgb).to(dev),
-             "refl0": torch.from_numpy(refl).to(dev)}
-        d["rgb"] = torch.empty_like(d["rgb0"])
-        d["refl"] = torch.empty_like(d["refl0"])
-        d["crgb"] = torch.empty((3, n), dtype=torch.int32, device=dev)
-        d["crefl"] = torch.empty((1, n), dtype=torch.int32, device=dev)
-        dv.append(d)
+    def to_dev(fr):
+        out = []
+        for xyz, rgb, refl in fr:
+            d = {"xyz": torch.from_numpy(xyz).to(dev), "rgb0": torch.from_numpy(rgb).to(dev),
+                 "refl0": torch.from_numpy(refl).to(dev)}
+            d["rgb"] = torch.empty_like(d["rgb0"])
+            d["refl"] = torch.empty_like(d["refl0"])
+            d["crgb"] = torch.empty((3, n), dtype=torch.int32, device=dev)
+            d["crefl"] = torch.empty((1, n), dtype=torch.int32, device=dev)
+            out.append(d)
+        return out
+
+    dv = to_dev(frames)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def dev_jobs(subset):
-        jobs = []
-        for d in subset:
-            jobs.append(lambda d=d: pb.attr_raht_encode_dev(
-                params, qpset, d["xyz"].data_ptr(), d["rgb"].data_ptr(), d["crgb"].data_ptr(), n, 3))
-            jobs.append(lambda d=d: pb.attr_raht_encode_dev(
-                params, qpset, d["xyz"].data_ptr(), d["refl"].data_ptr(), d["crefl"].data_ptr(), n, 1))
-        return jobs
+        # one call per frame: colour and reflectance in one pass
+        return [lambda d=d: pb.attr_raht_encode_multi_dev(
+            params, qpsets, d["xyz"].data_ptr(), [d["rgb"].data_ptr(), d["refl"].data_ptr()],
+            [d["crgb"].data_ptr(), d["crefl"].data_ptr()], n, [3, 1]) for d in subset]
 
     def run_jobs(jobs):
         for f in [pool.submit(j) for j in jobs]:
             f.result()
 
-    def prepare():
+    def prepare(subset):
         flush.fill_(1)
-        for d in dv:
+        for d in subset:
             d["rgb"].copy_(d["rgb0"])
             d["refl"].copy_(d["refl0"])
         torch.cuda.synchronize()
@@ -423,7 +450,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed_device_step(subset):
-        prepare()
+        prepare(subset)
         pb.time_begin()
         run_jobs(dev_jobs(subset))
         return pb.time_end()
@@ -437,27 +464,73 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = pb.kernel_launch_count()
-    total_ms = 0.0
-    for _ in range(args.steps):
-        total_ms += timed_device_step(dv)
+    step_ms = [timed_device_step(dv) for _ in range(args.steps)]
+    total_ms = float(sum(step_ms))
     launches = pb.kernel_launch_count() - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # latency of one frame alone (RGB and reflectance concurrently)
+    # latency of one frame alone
     single_ms = min(timed_device_step(dv[:1]) for _ in range(3))
 
-    # the dominant kernel timed alone: one attribute call at a time, CUDA
-    # events around every launch
+    # the dominant kernel timed alone: one call at a time, CUDA events around
+    # every launch
     pb.profile_reset()
     pb.profile_enable(True)
     prof_steps = 2
     for _ in range(prof_steps):
-        prepare()
+        prepare(dv[:1])
         for j in dev_jobs(dv[:1]):
             j()
     pb.profile_enable(False)
     prof = pb.profile_read()
+    gpu_frame0 = {k: dv[0][k].cpu().numpy() for k in ("rgb", "refl", "crgb", "crefl")}
+
+    # the decoder on the same frame (extra key): coefficients in, attributes out
+    dec = None
+    if rank == 0:
+        try:
+            d0 = dv[0]
+            drgb, drefl = torch.empty_like(d0["rgb"]), torch.empty_like(d0["refl"])
+            k = len(qpsets)
+
+            def dec_call():
+                QP_ = C.POINTER(pb.QpSet) * k
+                VP = C.c_void_p * k
+                pb._check(pb.lib().pccb200_attr_raht_decode_multi_dev(
+                    C.byref(params), C.c_int32(k), QP_(*[C.pointer(q) for q in qpsets]),
+                    C.c_void_p(d0["xyz"].data_ptr()), VP(drgb.data_ptr(), drefl.data_ptr()),
+                    (C.c_int32 * k)(3, 1), (C.c_int32 * k)(8, 8), C.c_int32(n),
+                    VP(d0["crgb"].data_ptr(), d0["crefl"].data_ptr())))
+
+            dec_call()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                pb.time_begin()
+                dec_call()
+                ts.append(pb.time_end())
+            ok = bool(torch.equal(drgb, d0["rgb"]) and torch.equal(drefl, d0["refl"]))
+            dec = {"single_frame_ms": min(ts), "mpoints_per_s": n / min(ts) / 1e3,
+                   "reproduces_encoder_reconstruction": ok}
+        except Exception as e:
+            dec = {"error": str(e)[:200]}
+
+    # the smooth attribute field of round 1 (zero runs thousands of coefficients
+    # long, RDOQ nearly idle), same geometry: extra key, not the headline
+    smooth = None
+    if rank == 0 and not args.no_smooth:
+        sframes = [make_frame(sd, textured=False) for sd in frame_seeds(rank, F)]
+        sdv = to_dev(sframes)
+        for _ in range(2):
+            timed_device_step(sdv)
+        sm = [timed_device_step(sdv) for _ in range(max(3, args.steps // 2))]
+        s1 = min(timed_device_step(sdv[:1]) for _ in range(3))
+        smooth = {"value": F * n / (sum(sm) / len(sm)) / 1e3, "unit": "Mpoints/s (this GPU)",
+                  "ms_per_step": sum(sm) / len(sm), "single_frame_ms": s1,
+                  "attribute_model": "smooth field + noise of +-8 (round 1's frame): 0.1 % of the "
+                                     "coefficient positions non-zero at qp 34"}
+        del sdv, sframes
 
     # ---- end to end: host-pointer C ABI, pinned host buffers ---------------
     hv = []
@@ -471,11 +544,8 @@ def run_ours(args):
         hv.append(h)
 
     def host_jobs():
-        jobs = []
-        for h in hv:
-            jobs.append(lambda h=h: pb.attr_raht_encode_into(params, qpset, h["xyz"], h["rgb"], h["crgb"]))
-            jobs.append(lambda h=h: pb.attr_raht_encode_into(params, qpset, h["xyz"], h["refl"], h["crefl"]))
-        return jobs
+        return [lambda h=h: pb.attr_raht_encode_multi_into(
+            params, qpsets, h["xyz"], [h["rgb"], h["refl"]], [h["crgb"], h["crefl"]]) for h in hv]
 
     def host_prepare():
         flush.fill_(1)
@@ -498,14 +568,120 @@ def run_ours(args):
         e2e_s += time.perf_counter() - t0
     barrier()
     xyz, rgb, refl = frames[0]
-    h2d = F * (2 * xyz.nbytes + rgb.nbytes + refl.nbytes)
+    h2d = F * (xyz.nbytes + rgb.nbytes + refl.nbytes)
     d2h = F * 2 * (rgb.nbytes + refl.nbytes)
+    e2e_equal_dev = bool(np.array_equal(hv[0]["crgb"].numpy(), gpu_frame0["crgb"])
+                         and np.array_equal(hv[0]["crefl"].numpy(), gpu_frame0["crefl"]))
 
+    extras = run_extras(args, pb, rank, world, params, qpset, frames[0], run_jobs)
+
+    per_rank = [total_ms / args.steps]
+    if distributed:
+        g = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev))
+        per_rank = [float(x[0]) / args.steps for x in g]
+        total_ms, e2e_s = max(float(x[0]) for x in g), max(float(x[1]) for x in g)
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        blk_ms, blk_launches = prof["block_transform"]
+        blk_ms_per_frame = blk_ms / prof_steps
+        achieved = ALG_BYTES_PER_POINT * n / (blk_ms_per_frame * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("block_transform_dram_bytes_per_frame")
+        line = {
+            "metric": METRIC,
+            "value": world * F * n * args.steps / (total_ms * 1e-3) / 1e6,
+            "unit": "Mpoints/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": workload_config(F),
+            "e2e": {"value": world * F * n * args.steps / e2e_s / 1e6, "unit": "Mpoints/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "result_checksum": checksum,
+                    "equals_device_resident_result": e2e_equal_dev},
+            "concurrency": f"{F} calls in flight per GPU (one CUDA stream each; colour and "
+                           f"reflectance of a frame are coded in one pass)",
+            "per_rank_ms_per_step": {"min": min(per_rank), "median": float(np.median(per_rank)),
+                                     "max": max(per_rank), "all": per_rank},
+            "numa_bound_cpus": numa_cpus,
+            "single_frame": {"ms": single_ms, "mpoints_per_s": n / single_ms / 1e3,
+                             "note": "one frame alone (RGB + reflectance in one pass)"},
+            "decoder": dec,
+            "smooth_frame": smooth,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm",
+                "kernel": "k_block_warp (top-down block transform; all stage launches of one "
+                          "frame: RGB + reflectance in one pass, timed alone)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": ALG_BYTES_PER_POINT * n,
+                "kernel_ms_per_frame": blk_ms_per_frame,
+                "kernel_launches_per_frame": blk_launches / prof_steps,
+                "note": "serial dependency chain (RDOQ zero-run state in coding order + sub-node "
+                        "prediction), not bandwidth bound; see DESIGN.md"},
+            "phase_ms_per_frame_alone": {k: v[0] / prof_steps for k, v in prof.items()},
+        }
+        line.update(extras)
+        # reported CPU baseline + parity: single N=1 run only (bounded: one frame)
+        if world == 1 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import pcc_testlib as tl
+
+            run, kind = load_cpu_impl()
+            cp, cq = tl.make_params(search_range=SEARCH_RANGE), tl.make_qpset(qp=QP, chroma_offset=CHROMA_OFFSET)
+            t0 = time.perf_counter()
+            c_rgb_rec, c_rgb = run(cp, cq, frames[0][0], frames[0][1])
+            c_refl_rec, c_refl = run(cp, cq, frames[0][0], frames[0][2])
+            secs = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": n / secs / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": kind,
+                "sample": f"1 frame of the same workload ({n} points, RGB + reflectance), "
+                          f"{secs:.2f} s on one host core; host: {host_cpu_model()}"}
+            # the same frame: the GPU's coefficients and reconstruction against the CPU's
+            parity = bool(np.array_equal(gpu_frame0["crgb"], c_rgb)
+                          and np.array_equal(gpu_frame0["crefl"], c_refl)
+                          and np.array_equal(gpu_frame0["rgb"], c_rgb_rec)
+                          and np.array_equal(gpu_frame0["refl"], c_refl_rec))
+            line["parity_checked"] = parity
+            line["parity_note"] = ("frame 0: coefficients and reconstruction of the GPU path "
+                                   f"bit-identical to the CPU {kind} (4 M coefficients + 4 M values)")
+            line["coefficients"] = coefficient_histogram([("rgb", c_rgb), ("reflectance", c_refl)])
+            if not parity:
+                line["parity_note"] = "MISMATCH between the GPU path and the CPU " + kind
+                emit_json(line)
+                raise SystemExit("bench.py: GPU result differs from the CPU reference")
+        emit_json(line)
+    pool.shutdown()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_extras(args, pb, rank, world, params, qpset, frame, run_jobs):
+    """Extra keys of the N=1 line (never the headline): the lifting path and the
+    rows either side of the transform."""
+    out = {}
+    if rank != 0 or args.no_lifting:
+        return out
+    xyz, rgb, refl = frame
     # ---- the lifting path (SURVEY.md 8d config 4 shape): LoD build + weights +
     # lifting + quantisation + reconstruction of a dense 1M-point surface slice,
-    # host-pointer ABI, reported beside the headline (extra key, not `value`)
-    lifting = None
-    if rank == 0 and not args.no_lifting:
+    # host-pointer ABI
+    try:
         from pcc_attr_b200.synth import cloud_shell
 
         lxyz, lrgb = cloud_shell(N_POINTS, bits=11, seed=40)
@@ -538,121 +714,32 @@ def run_ours(args):
             "mpoints_per_s_single": lxyz.shape[0] / single / 1e6,
             "mpoints_per_s_8_in_flight": lf * lxyz.shape[0] / batch / 1e6,
         }
-        liftref = os.path.join(ROOT, "oracle", "_ref", "libtmc13_lift.so")
-        if os.path.exists(liftref) and not args.no_cpu_baseline and world == 1:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import pcc_testlib as tl
+        out["lifting_path"] = lifting
+    except Exception as e:
+        out["lifting_path"] = {"error": str(e)[:200]}
 
-            t0 = time.perf_counter()
-            tl.ref_lift_encode(tl.make_lod_params(levels=12), tl.make_qpset(
-                qp=QP, chroma_offset=CHROMA_OFFSET, fixed_point_qp_offset=24), 1, lxyz, lrgb)
-            lifting["cpu_reference_ms_one_core"] = 1e3 * (time.perf_counter() - t0)
-            lifting["cpu_reference_note"] = ("the reference's own encodeColorsLift on one host core "
-                                             "(includes its entropy coding)")
-
-    # ---- the two rows either side of the transform:
-    # spherical positions before it, the entropy coder's symbols after it; one
-    # frame through the host-pointer ABI, reported as an extra key
-    adjacent = None
-    if rank == 0 and not args.no_lifting:
-        try:
-            theta = np.rint(np.tan(np.linspace(-0.43, 0.04, 64)) * (1 << 18)).astype(np.int32)
-            origin, weight = (0, 0, 0), (256, 640, 193128)
-            pb.attr_spherical_positions(origin, theta, weight, xyz)
-            t0 = time.perf_counter()
-            pb.attr_spherical_positions(origin, theta, weight, xyz)
-            sph = time.perf_counter() - t0
-            pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
-            t0 = time.perf_counter()
-            _, runs, _, _, _ = pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
-            sym = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            pb.attr_raht_encode(params, qpset, xyz, rgb)
-            plain = time.perf_counter() - t0
-            adjacent = {
-                "spherical_positions_ms": 1e3 * sph,
-                "spherical_positions_mpoints_per_s": xyz.shape[0] / sph / 1e6,
-                "rgb_encode_with_symbols_ms": 1e3 * sym,
-                "rgb_encode_with_planar_coefficients_ms": 1e3 * plain,
-                "symbols": int(len(runs)),
-                "d2h_bytes_symbols": int(len(runs)) * 16 + rgb.nbytes,
-                "d2h_bytes_planar": 2 * rgb.nbytes,
-                "note": "one 1M-point frame, host-pointer ABI, pageable buffers, wall clock",
-            }
-        except Exception as e:  # an extra: never take the headline down with it
-            adjacent = {"error": str(e)[:200]}
-
-    if distributed:
-        total_ms, e2e_s = reduce_timing([total_ms, e2e_s], dist, dev)
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt[0])
-
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        blk_ms, blk_launches = prof["block_transform"]
-        blk_ms_per_frame = blk_ms / prof_steps
-        achieved = ALG_BYTES_PER_POINT * n / (blk_ms_per_frame * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("block_transform_dram_bytes_per_frame")
-        cfg = workload_config()
-        cfg["frames_per_step_per_gpu"] = F
-        cfg["concurrency"] = f"{2 * F} attribute calls in flight per GPU (one CUDA stream each)"
-        line = {
-            "metric": METRIC,
-            "value": world * F * n * args.steps / (total_ms * 1e-3) / 1e6,
-            "unit": "Mpoints/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic",
-            "config": cfg,
-            "e2e": {"value": world * F * n * args.steps / e2e_s / 1e6, "unit": "Mpoints/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "result_checksum": checksum},
-            "single_frame": {"ms": single_ms, "mpoints_per_s": n / single_ms / 1e3,
-                             "note": "one frame alone: RGB and reflectance calls concurrent"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {
-                "bound": "hbm",
-                "kernel": "k_block_warp (top-down block transform; all stage launches of one "
-                          "RGB + one reflectance call, timed alone)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_frame": ALG_BYTES_PER_POINT * n,
-                "kernel_ms_per_frame": blk_ms_per_frame,
-                "kernel_launches_per_frame": blk_launches / prof_steps,
-                "note": "dependency-latency bound (RDOQ zero-run chain + sub-node prediction), "
-                        "not bandwidth bound; see DESIGN.md"},
-            "phase_ms_per_frame_alone": {k: v[0] / prof_steps for k, v in prof.items()},
+    # ---- the two rows either side of the transform
+    try:
+        theta = np.rint(np.tan(np.linspace(-0.43, 0.04, 64)) * (1 << 18)).astype(np.int32)
+        origin, weight = (0, 0, 0), (256, 640, 193128)
+        pb.attr_spherical_positions(origin, theta, weight, xyz)
+        t0 = time.perf_counter()
+        pb.attr_spherical_positions(origin, theta, weight, xyz)
+        sph = time.perf_counter() - t0
+        pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
+        t0 = time.perf_counter()
+        _, runs, _, _, _ = pb.attr_raht_encode_symbols(params, qpset, xyz, rgb)
+        sym = time.perf_counter() - t0
+        out["adjacent_rows"] = {
+            "spherical_positions_ms": 1e3 * sph,
+            "spherical_positions_mpoints_per_s": xyz.shape[0] / sph / 1e6,
+            "rgb_encode_with_symbols_ms": 1e3 * sym,
+            "symbols": int(len(runs)),
+            "note": "one 1M-point frame, host-pointer ABI, pageable buffers, wall clock",
         }
-        line["lifting_path"] = lifting
-        if adjacent is not None:
-            line["adjacent_rows"] = adjacent
-        # reported CPU baseline: single N=1 run only (bounded: one frame)
-        if world == 1 and not args.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import pcc_testlib as tl
-
-            run, kind = load_cpu_impl()
-            secs = cpu_frame_seconds(run, tl.make_params(search_range=SEARCH_RANGE),
-                                     tl.make_qpset(qp=QP, chroma_offset=CHROMA_OFFSET), frames[0])
-            line["cpu_baseline"] = {
-                "value": n / secs / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": kind,
-                "sample": f"1 frame of the same workload ({n} points, RGB + reflectance), "
-                          f"{secs:.2f} s on one host core; host: {host_cpu_model()}"}
-        emit_json(line)
-    pool.shutdown()
-    if distributed:
-        dist.destroy_process_group()
+    except Exception as e:  # an extra: never take the headline down with it
+        out["adjacent_rows"] = {"error": str(e)[:200]}
+    return out
 
 
 def main():
@@ -664,7 +751,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lifting", action="store_true", help="skip the extra lifting-path measurement")
-    ap.add_argument("--frames", type=int, default=16,
+    ap.add_argument("--no-smooth", action="store_true", help="skip the extra smooth-frame measurement")
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP,
                     help="independent frames in flight per GPU per step (intra coding: frames "
                          "are independent work units)")
     args = ap.parse_args()

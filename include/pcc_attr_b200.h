@@ -216,6 +216,46 @@ int pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
                                         int32_t num_slices,
                                         const int32_t* d_coeffs_in);
 
+/* Several attributes of one slice in ONE pass ----------------------------------
+ *
+ * The attributes of a slice are coded on the same positions
+ * (tmc3/encoder.cpp:1052-1240 loops over them; AttributeEncoder::encode is
+ * entered once per attribute): the Morton sort, the tree, the worklists, the
+ * neighbour searches, the weights and, above all, the chain of block
+ * dependencies are the same for all of them.  These entry points code up to
+ * two attributes with at most four components together (typically colour +
+ * reflectance): each keeps its own QpSet, coefficient planes and zero-run
+ * state, and the results are bit-identical to one call per attribute.
+ * Per-point qp offsets are not supported here (use the single-attribute
+ * calls); parameter combinations without a fused path (AC-coefficient qp
+ * offsets in the encoder) are coded attribute by attribute internally.
+ *
+ *   qpsets[s], attrs[s] (n x num_attrs[s], row-major, in/out), num_attrs[s],
+ *   bitdepths[s], coeffs[s] (num_attrs[s] planes of n) describe attribute s.
+ * The *_dev variants take device pointers for xyz, attrs[s] and coeffs[s]
+ * (the pointer arrays themselves are host arrays); see the stream-ordering
+ * note above. */
+int pccb200_attr_raht_encode_multi(const pccb200_raht_params* params, int32_t num_sets,
+                                   const pccb200_qpset* const* qpsets, const int32_t* xyz,
+                                   int32_t* const* attrs_inout, const int32_t* num_attrs,
+                                   const int32_t* bitdepths, int32_t n,
+                                   int32_t* const* coeffs_out);
+int pccb200_attr_raht_decode_multi(const pccb200_raht_params* params, int32_t num_sets,
+                                   const pccb200_qpset* const* qpsets, const int32_t* xyz,
+                                   int32_t* const* attrs_out, const int32_t* num_attrs,
+                                   const int32_t* bitdepths, int32_t n,
+                                   const int32_t* const* coeffs_in);
+int pccb200_attr_raht_encode_multi_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                       const pccb200_qpset* const* qpsets,
+                                       const int32_t* d_xyz, int32_t* const* d_attrs_inout,
+                                       const int32_t* num_attrs, const int32_t* bitdepths,
+                                       int32_t n, int32_t* const* d_coeffs_out);
+int pccb200_attr_raht_decode_multi_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                       const pccb200_qpset* const* qpsets,
+                                       const int32_t* d_xyz, int32_t* const* d_attrs_out,
+                                       const int32_t* num_attrs, const int32_t* bitdepths,
+                                       int32_t n, const int32_t* const* d_coeffs_in);
+
 /* Per-phase device timing (CUDA events around every kernel launch on
  * the call's stream).  Phases: 0 Morton keys + radix sort, 1 tree build
  * (histogram, compaction, leaf / merge kernels), 2 block transform (the
@@ -346,6 +386,38 @@ int pccb200_attr_lift_decode(const pccb200_lod_params* lod,
                              int32_t* attrs_out, int32_t num_attrs, int32_t n,
                              int32_t bitdepth, const int32_t* values_in,
                              const int8_t* lcp_coeffs);
+
+/* Levels of detail kept across the attributes of a slice ------------------------
+ *
+ * AttributeEncoder / AttributeDecoder keep the LoDs of a slice
+ * (tmc3/AttributeEncoder.h:183 `_lods`) and rebuild them only when the next
+ * attribute's parameters differ (AttributeLods::isReusable,
+ * tmc3/AttributeCommon.cpp:76-140; caller tmc3/encoder.cpp:1209-1210).  The
+ * handle owns the device-resident predictors, the predictor order and the
+ * quantisation weights of one slice; the colour call and the reflectance
+ * call of the slice then run the lifting passes only. */
+typedef struct pccb200_lod_handle_s* pccb200_lod_handle;
+
+/* Builds the levels of detail of xyz (N x 3, host) on the selected device. */
+int pccb200_lod_create(const pccb200_lod_params* params, const int32_t* xyz, int32_t n,
+                       pccb200_lod_handle* handle_out);
+void pccb200_lod_destroy(pccb200_lod_handle handle);
+/* 1 if LoDs built with the handle's parameters serve `params` as well (the
+ * comparisons of AttributeLods::isReusable that this structure carries), else 0. */
+int pccb200_lod_reusable(pccb200_lod_handle handle, const pccb200_lod_params* params);
+/* number of points / of LoDs; num_points_in_lod_out: PCCB200_MAX_LODS entries or NULL */
+int pccb200_lod_info(pccb200_lod_handle handle, int32_t* n_out, int32_t* lod_count_out,
+                     uint32_t* num_points_in_lod_out);
+/* As pccb200_attr_lift_encode / _decode without positions and LoD
+ * parameters: the handle's. */
+int pccb200_attr_lift_encode_lod(pccb200_lod_handle handle, const pccb200_qpset* qpset,
+                                 int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                 int32_t* attrs_inout, int32_t num_attrs, int32_t bitdepth,
+                                 int32_t* values_out, int8_t* lcp_coeffs_out);
+int pccb200_attr_lift_decode_lod(pccb200_lod_handle handle, const pccb200_qpset* qpset,
+                                 int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                 int32_t* attrs_out, int32_t num_attrs, int32_t bitdepth,
+                                 const int32_t* values_in, const int8_t* lcp_coeffs);
 
 /* ---------------------------------------------------------------------------
  * Spherical coordinates for attribute coding of LiDAR slices (the step before

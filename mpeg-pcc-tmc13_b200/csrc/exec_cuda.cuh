@@ -488,7 +488,7 @@ struct DeviceExec {
         v = 0;
       return v < 1 ? 1 : v;
     }();
-    const int64_t perCta = kWarpBlockThreads / 32;
+    const int64_t perCta = kWarpBlockThreads / 32;  // (at least one ticket per warp)
     int64_t blocks = (nBlocks + perCta - 1) / perCta;
     // calls in flight share the machine: the persistent grid of each takes
     // its part (sampled at launch time).  Together the persistent grids of the
@@ -544,14 +544,21 @@ struct DeviceExec {
     }
     WarpBlockArgs a = {};
     a.cfg = fn.cfg;
-    a.qt = fn.qt;
+    a.numSets = 1;
+    AttrSet& st = a.set[0];
+    st.A = fn.cfg.A;
+    st.base = 0;
+    st.maxQp = fn.cfg.maxQp;
+    st.fixedPointQpOffset = fn.cfg.fixedPointQpOffset;
+    st.numAcLayers = fn.cfg.numAcLayers;
+    st.qpLayer = fn.qpLayer;
+    st.acLayer = fn.acLayer;
+    st.qt = fn.qt;
+    st.coef = fn.coef;
+    st.coefStride = fn.coefStride;
     a.S = fn.S;
     a.P = fn.P;
-    a.coef = fn.coef;
-    a.coefStride = fn.coefStride;
     a.coefBase = fn.coefBase;
-    a.qpLayer = fn.qpLayer;
-    a.acLayer = fn.acLayer;
     a.predInLvl = fn.predInLvl;
     raht_ab(1, 1, a.ab11a, a.ab11b);
     int* dCount = alloc<int>(1);
@@ -572,14 +579,14 @@ struct DeviceExec {
     }
     TzRegion hr;
     hr.words = fn.tz;
-    hr.lists = fn.tz ? alloc<int>((size_t(nBlocks) + 1) * 8) : nullptr;
+    hr.lists = fn.tz ? alloc<int>((size_t(nBlocks) + 1) * 2) : nullptr;
     hr.count = dCount;
     a.stageIdx = numRegions;
     upload(dRegions + numRegions, &hr, sizeof(TzRegion));
     numRegions++;
-    a.regions = dRegions;
-    a.words = hr.words;
-    a.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+    st.regions = dRegions;
+    st.words = hr.words;
+    st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
     static const int pollNs = [] {
       const char* e = getenv("PCCB200_POLL_NS");
       return e ? atoi(e) : 32;

@@ -199,6 +199,37 @@ k_gather_rows(const T* __restrict__ in, const int32_t* __restrict__ order, int64
   }
 }
 
+// out[i*outStride + outOff + k] = in[order[i]*A + k]  (one attribute of several
+// into the interleaved rows of a multi-attribute pass)
+__global__ void __launch_bounds__(256)
+k_gather_rows_strided(const int32_t* __restrict__ in, const int32_t* __restrict__ order,
+                      int64_t n, int A, int32_t* __restrict__ out, int outStride, int outOff)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t src = order[i];
+    for (int k = 0; k < A; k++)
+      out[i * outStride + outOff + k] = in[src * A + k];
+  }
+}
+
+// out[order[i]*A + k] = clip(in[i*inStride + inOff + k], 0, clipMax)
+__global__ void __launch_bounds__(256)
+k_scatter_rows_clip_strided(const int32_t* __restrict__ in, int inStride, int inOff,
+                            const int32_t* __restrict__ order, int64_t n, int A,
+                            int32_t clipMax, int32_t* __restrict__ out)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t dst = order[i];
+    for (int k = 0; k < A; k++) {
+      int32_t v = in[i * inStride + inOff + k];
+      v = v < 0 ? 0 : (v > clipMax ? clipMax : v);
+      out[dst * A + k] = v;
+    }
+  }
+}
+
 // out[order[i]*A + k] = clip(in[i*A + k], 0, clipMax)
 __global__ void __launch_bounds__(256)
 k_scatter_rows_clip(const int32_t* __restrict__ in, const int32_t* __restrict__ order,

@@ -358,6 +358,47 @@ attr_raht_slice(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
   return PCCB200_OK;
 }
 
+// one slice, several attributes on the same positions in one pass: one sort,
+// one tree, one dependency chain.  Pointers as in attr_raht_slice, one per set.
+// PCCB200_ERR_UNSUPPORTED: this parameter combination has no fused path.
+int
+attr_raht_slice_multi(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
+                      int numSets, const pccb200_qpset* const* qpsets, const int32_t* dXyz,
+                      const int32_t* const* dAttrsIn, int32_t* const* dAttrsOut, const int* A,
+                      const int* bitdepth, int n, int32_t* const* dCoef, const int64_t* coefStride)
+{
+  int AT = 0;
+  for (int s = 0; s < numSets; s++)
+    AT += A[s];
+  int64_t* dKeys = ex.alloc<int64_t>(size_t(n));
+  int32_t* dOrder = ex.alloc<int32_t>(size_t(n));
+  int32_t* dAttrs = ex.alloc<int32_t>(size_t(n) * AT);
+  device_morton_sort(ex, dXyz, n, dKeys, dOrder);
+  const unsigned g = grid_for(n, ex.numSMs);
+  ex.phase(kPhaseGather);
+  RahtSetIO io[2];
+  for (int s = 0, base = 0; s < numSets; base += A[s], s++) {
+    if (forward) {
+      DeviceExec::Scope sc(ex);
+      k_gather_rows_strided<<<g, 256, 0, ex.stream>>>(dAttrsIn[s], dOrder, n, A[s], dAttrs, AT, base);
+      g_launchCount++;
+    }
+    io[s] = RahtSetIO{qpsets[s], A[s], dCoef[s], coefStride[s]};
+  }
+  int rc = raht_run_sets(ex, *params, numSets, io, forward, dKeys, dAttrs, nullptr, n);
+  if (rc != PCCB200_OK)
+    return rc == PCCB200_ERR_UNSUPPORTED ? rc : fail(rc, "invalid parameters");
+  ex.phase(kPhaseGather);
+  for (int s = 0, base = 0; s < numSets; base += A[s], s++) {
+    DeviceExec::Scope sc(ex);
+    k_scatter_rows_clip_strided<<<g, 256, 0, ex.stream>>>(dAttrs, AT, base, dOrder, n, A[s],
+                                                          (1 << bitdepth[s]) - 1, dAttrsOut[s]);
+    g_launchCount++;
+  }
+  PCC_CUDA_CHECK(cudaGetLastError());
+  return PCCB200_OK;
+}
+
 int
 check_slices(const void* params, const void* qpset, const void* xyz, const void* attrs,
              const void* coeffs, int A, int bitdepth, const int64_t* sliceOffsets,
@@ -436,6 +477,83 @@ attr_raht_common_dev(bool forward, const pccb200_raht_params* params,
                              dCoef + o, total);
     });
   });
+}
+
+int
+check_multi(const void* params, int numSets, const pccb200_qpset* const* qpsets, const void* xyz,
+            const void* const* attrs, const int32_t* A, const int32_t* bitdepth,
+            const void* const* coeffs, int64_t n)
+{
+  if (!params || !qpsets || !xyz || !attrs || !A || !bitdepth || !coeffs || n <= 0
+      || n > INT32_MAX || numSets < 1 || numSets > 2)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  int total = 0;
+  for (int s = 0; s < numSets; s++) {
+    if (!qpsets[s] || !attrs[s] || !coeffs[s] || A[s] < 1 || A[s] > 3 || bitdepth[s] < 1
+        || bitdepth[s] > 16)
+      return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad attribute description");
+    total += A[s];
+  }
+  if (total > 4)
+    return fail(PCCB200_ERR_INVALID_ARG, "more than four components in one pass");
+  return PCCB200_OK;
+}
+
+// Several attributes of one slice.  Fused pass where the parameters allow it,
+// otherwise one pass per attribute (same results either way).
+int
+attr_raht_multi_common(bool forward, bool device, const pccb200_raht_params* params, int numSets,
+                       const pccb200_qpset* const* qpsets, const int32_t* xyz,
+                       int32_t* const* attrs, const int32_t* A, const int32_t* bitdepth, int n,
+                       int32_t* const* coeffs)
+{
+  int rc = check_multi(params, numSets, qpsets, xyz, reinterpret_cast<const void* const*>(attrs),
+                       A, bitdepth, reinterpret_cast<const void* const*>(coeffs), n);
+  if (rc != PCCB200_OK)
+    return rc;
+  rc = with_device([&](DeviceExec& ex) -> int {
+    const int32_t* dXyz = device ? xyz : to_device(ex, xyz, size_t(n) * 3);
+    int32_t* dIn[2];
+    int32_t* dOut[2];
+    int32_t* dCoef[2];
+    int64_t stride[2];
+    for (int s = 0; s < numSets; s++) {
+      stride[s] = n;
+      if (device) {
+        dIn[s] = dOut[s] = attrs[s];
+        dCoef[s] = coeffs[s];
+      } else {
+        dIn[s] = forward ? to_device(ex, attrs[s], size_t(n) * A[s]) : nullptr;
+        dOut[s] = ex.alloc<int32_t>(size_t(n) * A[s]);
+        dCoef[s] = forward ? ex.alloc<int32_t>(size_t(n) * A[s])
+                           : to_device(ex, coeffs[s], size_t(n) * A[s]);
+      }
+    }
+    int rc2 = attr_raht_slice_multi(ex, forward, params, numSets, qpsets, dXyz, dIn, dOut, A,
+                                    bitdepth, n, dCoef, stride);
+    if (rc2 != PCCB200_OK)
+      return rc2;
+    if (!device)
+      for (int s = 0; s < numSets; s++) {
+        to_host(ex, attrs[s], dOut[s], size_t(n) * A[s]);
+        if (forward)
+          to_host(ex, coeffs[s], dCoef[s], size_t(n) * A[s]);
+      }
+    return PCCB200_OK;
+  });
+  if (rc != PCCB200_ERR_UNSUPPORTED)
+    return rc;
+  // no fused path for these parameters: attribute by attribute
+  for (int s = 0; s < numSets; s++) {
+    const int64_t offs[2] = {0, n};
+    rc = device ? attr_raht_common_dev(forward, params, qpsets[s], nullptr, xyz, attrs[s], A[s],
+                                       bitdepth[s], offs, 1, coeffs[s])
+                : attr_raht_common(forward, params, qpsets[s], nullptr, xyz, attrs[s], A[s],
+                                   bitdepth[s], offs, 1, coeffs[s]);
+    if (rc != PCCB200_OK)
+      return rc;
+  }
+  return PCCB200_OK;
 }
 
 }  // namespace
@@ -605,6 +723,52 @@ pccb200_attr_raht_decode_slices_dev(const pccb200_raht_params* params,
                               num_attrs, bitdepth, slice_offsets, num_slices,
                               const_cast<int32_t*>(d_coeffs_in));
 }
+
+int
+pccb200_attr_raht_encode_multi(const pccb200_raht_params* params, int32_t num_sets,
+                               const pccb200_qpset* const* qpsets, const int32_t* xyz,
+                               int32_t* const* attrs_inout, const int32_t* num_attrs,
+                               const int32_t* bitdepths, int32_t n, int32_t* const* coeffs_out)
+{
+  return attr_raht_multi_common(true, false, params, num_sets, qpsets, xyz, attrs_inout,
+                                num_attrs, bitdepths, n, coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode_multi(const pccb200_raht_params* params, int32_t num_sets,
+                               const pccb200_qpset* const* qpsets, const int32_t* xyz,
+                               int32_t* const* attrs_out, const int32_t* num_attrs,
+                               const int32_t* bitdepths, int32_t n,
+                               const int32_t* const* coeffs_in)
+{
+  return attr_raht_multi_common(false, false, params, num_sets, qpsets, xyz, attrs_out,
+                                num_attrs, bitdepths, n,
+                                const_cast<int32_t* const*>(coeffs_in));
+}
+
+int
+pccb200_attr_raht_encode_multi_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                   const pccb200_qpset* const* qpsets, const int32_t* d_xyz,
+                                   int32_t* const* d_attrs_inout, const int32_t* num_attrs,
+                                   const int32_t* bitdepths, int32_t n,
+                                   int32_t* const* d_coeffs_out)
+{
+  return attr_raht_multi_common(true, true, params, num_sets, qpsets, d_xyz, d_attrs_inout,
+                                num_attrs, bitdepths, n, d_coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode_multi_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                   const pccb200_qpset* const* qpsets, const int32_t* d_xyz,
+                                   int32_t* const* d_attrs_out, const int32_t* num_attrs,
+                                   const int32_t* bitdepths, int32_t n,
+                                   const int32_t* const* d_coeffs_in)
+{
+  return attr_raht_multi_common(false, true, params, num_sets, qpsets, d_xyz, d_attrs_out,
+                                num_attrs, bitdepths, n,
+                                const_cast<int32_t* const*>(d_coeffs_in));
+}
+
 
 // Device-side timing across all lanes: begin() records an event that every
 // lane's stream waits for; end() records one event that waits for every
@@ -841,6 +1005,176 @@ attr_lift_common(bool forward, const pccb200_lod_params* lod, const pccb200_qpse
     for (int l = 0; l < lod->num_detail_levels && l < PCCB200_MAX_LODS; l++)
       lcp[l] = lcpLocal[l];
   return rc;
+}
+
+}  // extern "C"
+
+struct pccb200_lod_handle_s {
+  int device;
+  pccb200_lod_params params;
+  pccb200::LodState st;
+  void* block;  // one device allocation behind preds / idx / qw
+};
+
+namespace {
+
+int
+attr_lift_lod_common(bool forward, pccb200_lod_handle h, const pccb200_qpset* qpset,
+                     int32_t lcpEnabled, const int32_t* qpo, int32_t* attrs, int32_t A,
+                     int32_t bitdepth, int32_t* values, int8_t* lcp)
+{
+  if (!h || !qpset || !attrs || !values || (A != 1 && A != 3) || bitdepth < 1 || bitdepth > 16)
+    return pccb200::fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  if (h->device != pccb200::ctx().device)
+    return pccb200::fail(PCCB200_ERR_INVALID_ARG, "handle belongs to another device");
+  const int n = h->st.n;
+  const int levels = h->params.num_detail_levels;
+  int8_t lcpLocal[PCCB200_MAX_LODS + 1] = {};
+  if (!forward && lcpEnabled && A == 3) {
+    if (!lcp)
+      return pccb200::fail(PCCB200_ERR_INVALID_ARG, "lcp coefficients missing");
+    for (int l = 0; l < levels && l < PCCB200_MAX_LODS; l++)
+      lcpLocal[l] = lcp[l];
+  }
+  int rc = pccb200::with_device([&](pccb200::DeviceExec& ex) -> int {
+    int32_t* dIn = forward ? pccb200::to_device(ex, attrs, size_t(n) * A) : nullptr;
+    int32_t* dQpoIn = qpo ? pccb200::to_device(ex, qpo, size_t(n) * 2) : nullptr;
+    int32_t* dV = forward ? ex.alloc<int32_t>(size_t(n) * A)
+                          : pccb200::to_device(ex, values, size_t(n) * A);
+    int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+    int rc2 = pccb200::attr_lift_on_lods(ex, forward, h->st, *qpset, lcpEnabled != 0, dQpoIn, dIn,
+                                         dOut, A, bitdepth, dV, lcpLocal);
+    if (rc2 != PCCB200_OK)
+      return pccb200::fail(rc2, rc2 == PCCB200_ERR_UNSUPPORTED
+                                  ? "a predictor references its own level of detail"
+                                  : "invalid lifting parameters");
+    pccb200::to_host(ex, attrs, dOut, size_t(n) * A);
+    if (forward)
+      pccb200::to_host(ex, values, dV, size_t(n) * A);
+    return PCCB200_OK;
+  });
+  if (rc == PCCB200_OK && forward && lcp)
+    for (int l = 0; l < levels && l < PCCB200_MAX_LODS; l++)
+      lcp[l] = lcpLocal[l];
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int
+pccb200_lod_create(const pccb200_lod_params* params, const int32_t* xyz, int32_t n,
+                   pccb200_lod_handle* handle_out)
+{
+  if (!params || !xyz || !handle_out || n <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  *handle_out = nullptr;
+  pccb200_lod_handle h = new (std::nothrow) pccb200_lod_handle_s();
+  if (!h)
+    return fail(PCCB200_ERR_NOMEM, "host allocation failed");
+  h->params = *params;
+  h->block = nullptr;
+  int rc = with_device([&](DeviceExec& ex) -> int {
+    h->device = ctx().device;
+    const size_t szP = (size_t(n) * sizeof(pccb200_predictor) + 255) & ~size_t(255);
+    const size_t szQ = (size_t(n) * sizeof(uint64_t) + 255) & ~size_t(255);
+    const size_t szI = (size_t(n) * sizeof(uint32_t) + 255) & ~size_t(255);
+    PCC_CUDA_CHECK(cudaMalloc(&h->block, szP + szQ + szI));
+    char* b = static_cast<char*>(h->block);
+    h->st.preds = reinterpret_cast<pccb200_predictor*>(b);
+    h->st.qw = reinterpret_cast<uint64_t*>(b + szP);
+    h->st.idx = reinterpret_cast<uint32_t*>(b + szP + szQ);
+    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
+    int rc2 = lod_state_build(ex, *params, dXyz, n, h->st);
+    if (rc2 != PCCB200_OK)
+      return fail(rc2, "invalid LoD parameters");
+    return PCCB200_OK;
+  });
+  if (rc != PCCB200_OK) {
+    if (h->block)
+      cudaFree(h->block);
+    delete h;
+    return rc;
+  }
+  *handle_out = h;
+  return PCCB200_OK;
+}
+
+void
+pccb200_lod_destroy(pccb200_lod_handle handle)
+{
+  if (!handle)
+    return;
+  if (handle->block) {
+    cudaSetDevice(handle->device);
+    cudaFree(handle->block);
+  }
+  delete handle;
+}
+
+int
+pccb200_lod_reusable(pccb200_lod_handle h, const pccb200_lod_params* p)
+{
+  if (!h || !p)
+    return 0;
+  const pccb200_lod_params& a = h->params;
+  // the order of AttributeLods::isReusable (tmc3/AttributeCommon.cpp:76-140)
+  if (a.num_pred_nearest_neighbours != p->num_pred_nearest_neighbours
+      || a.inter_lod_search_range != p->inter_lod_search_range
+      || a.intra_lod_search_range != p->intra_lod_search_range
+      || a.num_detail_levels != p->num_detail_levels)
+    return 0;
+  for (int k = 0; k < 3; k++)
+    if (a.lod_neigh_bias[k] != p->lod_neigh_bias[k])
+      return 0;
+  if (a.lod_decimation_type != p->lod_decimation_type || a.dist2 != p->dist2)
+    return 0;
+  for (int l = 0; l < PCCB200_MAX_LODS; l++)
+    if (a.lod_sampling_period[l] != p->lod_sampling_period[l])
+      return 0;
+  if (a.intra_lod_prediction_skip_layers != p->intra_lod_prediction_skip_layers
+      || a.pred_weight_blending != p->pred_weight_blending
+      || a.prediction_with_distribution != p->prediction_with_distribution)
+    return 0;
+  return 1;
+}
+
+int
+pccb200_lod_info(pccb200_lod_handle h, int32_t* n_out, int32_t* lod_count_out,
+                 uint32_t* num_points_in_lod_out)
+{
+  if (!h)
+    return fail(PCCB200_ERR_INVALID_ARG, "null handle");
+  if (n_out)
+    *n_out = h->st.n;
+  if (lod_count_out)
+    *lod_count_out = h->st.lodCount;
+  if (num_points_in_lod_out)
+    for (int l = 0; l < PCCB200_MAX_LODS; l++)
+      num_points_in_lod_out[l] = l < h->st.lodCount ? h->st.npl[l] : 0;
+  return PCCB200_OK;
+}
+
+int
+pccb200_attr_lift_encode_lod(pccb200_lod_handle handle, const pccb200_qpset* qpset,
+                             int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                             int32_t* attrs_inout, int32_t num_attrs, int32_t bitdepth,
+                             int32_t* values_out, int8_t* lcp_coeffs_out)
+{
+  return attr_lift_lod_common(true, handle, qpset, lcp_enabled, point_qp_offsets, attrs_inout,
+                              num_attrs, bitdepth, values_out, lcp_coeffs_out);
+}
+
+int
+pccb200_attr_lift_decode_lod(pccb200_lod_handle handle, const pccb200_qpset* qpset,
+                             int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                             int32_t* attrs_out, int32_t num_attrs, int32_t bitdepth,
+                             const int32_t* values_in, const int8_t* lcp_coeffs)
+{
+  return attr_lift_lod_common(false, handle, qpset, lcp_enabled, point_qp_offsets, attrs_out,
+                              num_attrs, bitdepth, const_cast<int32_t*>(values_in),
+                              const_cast<int8_t*>(lcp_coeffs));
 }
 
 int

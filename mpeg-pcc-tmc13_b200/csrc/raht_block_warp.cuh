@@ -23,26 +23,40 @@
 
 namespace pccb200 {
 
-struct WarpBlockArgs {
-  RahtConfig cfg;
+// One attribute of the pass.  Attributes coded on the same positions share
+// everything that follows from geometry (tree, worklists, neighbour tables,
+// weights, butterfly constants, the dependency chain); each keeps its own
+// quantisers, prediction range test, coefficient planes and zero-run stream.
+// Component rows of the warp (lane >> 3): [base, base + A).
+struct AttrSet {
+  int A;     // components (1..3)
+  int base;  // first component row
+  int maxQp, fixedPointQpOffset, numAcLayers;
+  int qpLayer, acLayer;  // of the current stage
   const QpTables* qt;
+  int32_t* coef;         // planar coefficients, component kk at kk * coefStride
+  int64_t coefStride;
+  const struct TzRegion* regions;  // zero-run words/lists of every stage so far
+  int* words;                      // regions[stageIdx].words / .lists (kernel parameters:
+  unsigned long long* lists;       //   no load on the critical path)
+};
+
+constexpr int kMaxSets = 2;
+
+struct WarpBlockArgs {
+  RahtConfig cfg;     // cfg.A = components of all sets together (<= 4)
+  int numSets;
+  AttrSet set[kMaxSets];
   Stage S;
   Stage P;            // P.n == 0: root block
-  int32_t* coef;
-  int64_t coefStride;
   int64_t coefBase;
-  int qpLayer;
-  int acLayer;
   int predInLvl;
   const int32_t* worklist;  // block indices in Morton order (null for the root)
   int32_t* geom;            // kGeomStride ints per worklist entry (see k_block_geom)
   const int* count;         // number of worklist entries (device memory)
   int64_t ab11a, ab11b;     // RahtKernel(1, 1), the commonest butterfly
-  const struct TzRegion* regions;  // zero-run words/lists of every stage so far
-  int stageIdx;                    // index of this stage in regions (0 = root)
-  int* words;                      // regions[stageIdx].words / .lists (kernel parameters:
-  unsigned long long* lists;       //   no load on the critical path)
-  int pollNs;                      // sleep between polls of a value still being produced
+  int stageIdx;             // index of this stage in the sets' regions (0 = root)
+  int pollNs;               // sleep between polls of a value still being produced
   // wavefront schedule (raht_wave.cuh): ticket i runs the block of row
   // order[i] (worklist rank + orderBase), rows sorted by dependency level
   const int32_t* order;
@@ -205,52 +219,83 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 // classification of earlier blocks (this stage, then earlier stages); waits
 // only for blocks that have not classified their coefficients yet, never for
 // another block's own answer (whatever a block publishes later is consistent
-// with its list, so lanes that observe different words still agree).
+// with its list, so the answer does not depend on when a word is read).
+//
+// Called by all 32 lanes with the same arguments; the lanes fetch
+// the state words (and lists) of 32 predecessors per round trip, then every
+// lane walks over them in registers.  On textured content a block deep in
+// the window of tickets in flight has hundreds to thousands of classified
+// but unresolved predecessors behind it; walking them one L2 round trip at a
+// time made the stage as slow as a serial chain (measured: 35 times the time
+// of the smooth frame).
+//
+// The walk keeps d = positions that still have to be verified.  A block of
+// v coefficients with the soft ones at offsets k (from its end) turns d into
+// R - v, R = the reach of the chain "k <= R  =>  R = max(R, k + threshold_k)"
+// started at R = d; R <= v ends the walk with "yes".
 __device__ __forceinline__ bool
-tz_run_at_least(const WarpBlockArgs& a, int t, int need)
+tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, const int t,
+                const int need, const int lane)
 {
   if (need <= 0)
     return true;
-  int req = need;  // positions 1..req behind the block must not reset the run
-  int acc = 0;     // positions already verified
-  int s = a.stageIdx;
-  const int* words = a.words;
-  const unsigned long long* lists = a.lists;
+  int d = need;
+  int s = stageIdx;
+  const int* words = st.words;
+  const unsigned long long* lists = st.lists;
   int u = t - 1;
   for (;;) {
     if (u < 0) {
       if (--s < 0)
-        return acc >= req;  // start of the call: the counter starts at 0
-      const TzRegion rg = a.regions[s];
+        return false;  // start of the call: the counter starts at 0 (and d > 0 here)
+      const TzRegion rg = st.regions[s];
       words = rg.words;
       lists = reinterpret_cast<const unsigned long long*>(rg.lists);
       u = *rg.count - 1;
       continue;
     }
-    int w;
-    while (tz_status(w = ld_acquire(&words[u + 1])) == kTzNone)
-      __nanosleep(a.pollNs);
-    const int st = tz_status(w), v = tz_value(w);
-    if (st == kTzExit)
-      return v + acc >= req;
-    if (st == kTzClassified) {
-      const unsigned long long L = lists[u + 1];
-      for (int i = v - 1; i >= 0; i--) {
-        const int pos = acc + (v - i);
-        if (pos > req)
-          return true;
-        const int code = int((L >> (6 * i)) & 63);
-        if (code >= 3) {
-          const int li = thr_decode(code);
-          if (pos + li > req)
-            req = pos + li;
+    const int idx = u - lane;
+    const int w = idx >= 0 ? ld_acquire(&words[idx + 1]) : 0;
+    const uint32_t stop = __ballot_sync(0xffffffffu, idx < 0 || tz_status(w) == kTzNone);
+    const int usable = stop ? __ffs(stop) - 1 : 32;
+    if (usable == 0) {  // the nearest predecessor has not published anything yet
+      __nanosleep(pollNs);
+      continue;
+    }
+    // this lane's block: its list and the offsets of its soft coefficients
+    const int v = tz_value(w);
+    unsigned long long L = 0;
+    uint32_t sm = 0;
+    if (lane < usable && tz_status(w) == kTzClassified) {
+      L = lists[idx + 1];
+#pragma unroll
+      for (int k = 1; k <= 8; k++)
+        if (k <= v && ((L >> (6 * (v - k))) & 63) >= 3)
+          sm |= 1u << (k - 1);
+    }
+    for (int i = 0; i < usable; i++) {
+      const int wi = __shfl_sync(0xffffffffu, w, i);
+      const int sti = tz_status(wi), vi = tz_value(wi);
+      if (sti == kTzExit)
+        return vi >= d;
+      uint32_t m = __shfl_sync(0xffffffffu, sm, i);
+      int R = d;
+      if (m) {
+        const unsigned long long Li = (unsigned long long)shfl_i64((int64_t)L, i);
+        while (m) {
+          const int k = __ffs(m);
+          m &= m - 1;
+          if (k > R)
+            break;
+          const int r = k + thr_decode(int((Li >> (6 * (vi - k))) & 63));
+          R = r > R ? r : R;
         }
       }
+      if (R <= vi)
+        return true;
+      d = R - vi;
     }
-    acc += v;
-    if (acc >= req)
-      return true;
-    u--;
+    u -= usable;
   }
 }
 
@@ -268,10 +313,19 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   const RahtConfig& cfg = a.cfg;
   const Stage& S = a.S;
   const Stage& P = a.P;
-  const int A = cfg.A;
+  const int A = cfg.A;  // component rows in use (all sets)
   const int j = lane & 7;
   const int k = lane >> 3;
   const bool act = k < A;
+  // the attribute this lane's component belongs to
+  const int base1 = a.set[0].A;  // first row of the second set
+  const int si = (a.numSets > 1 && k >= base1) ? 1 : 0;
+  const AttrSet& my = a.set[si];
+  const int kk = k - my.base;                                    // component within its set
+  const uint32_t members = ((1u << (8 * my.A)) - 1) << (8 * my.base);  // lanes of the set
+  // lanes of unused rows form a group of their own in the per-set reductions
+  const uint32_t group = act ? members : ~((1u << (8 * A)) - 1);
+  const bool speaker = lane == 8 * my.base;  // publishes the set's zero-run words
   const bool root = P.n == 0;
   const bool haar = cfg.haar != 0;
   const bool ext = cfg.ext != 0;
@@ -292,14 +346,16 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   //-- prediction gating: neighbour indices and count come from k_block_geom;
   //   lane i < 19 fetches what the prediction needs of neighbour i
   bool enablePred = false;
-  int64_t nv0 = 0, nv1 = 0, nv2 = 0;  // its reconstruction at the parent stage
+  int64_t nv0 = 0, nv1 = 0, nv2 = 0, nv3 = 0;  // its reconstruction at the parent stage
   uint32_t nocc = 0;                  // its occupancy, if its children may be used
   int nfirst = 0;                     // and its first child
-  uint32_t validMask = 0;             // neighbours that contribute
+  uint32_t validMask = 0;             // neighbours that contribute (to this lane's attribute)
+  uint32_t validAny = 0;              // ... to any attribute
+  int nq = -1;                        // its index in the parent stage
   if (a.predInLvl) {
     const int g = lane < kGeomStride ? a.geom[size_t(t) * kGeomStride + lane] : -1;
     const int count = __shfl_sync(0xffffffffu, g, 19) & 0xff;
-    const int nq = lane < 19 ? g : -1;
+    nq = lane < 19 ? g : -1;
     enablePred = count >= cfg.thr1 && __shfl_sync(0xffffffffu, g, 0) >= 0;
     if (enablePred) {
       const int parentOnly = cfg.subnode ? 7 : 19;
@@ -309,17 +365,30 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
           nv1 = P.rec[size_t(nq) * A + 1];
         if (A > 2)
           nv2 = P.rec[size_t(nq) * A + 2];
+        if (A > 3)
+          nv3 = P.rec[size_t(nq) * A + 3];
         if (lane >= parentOnly && nq < p) {
           nocc = P.occ[nq];
           nfirst = P.first[nq];
         }
       }
       // neighbours whose first component is out of range of the block's own
-      // parent are ignored (RAHT.cpp:392-404)
+      // parent are ignored (RAHT.cpp:392-404): one test per attribute
       const int64_t self = shfl_i64(nv0, 0);
       const int64_t limLow = 2 * self, limHigh = 25 * self;
       const bool ok = nq >= 0 && (lane == 0 || (10 * nv0 > limLow && 10 * nv0 < limHigh));
       validMask = __ballot_sync(0xffffffffu, ok);
+      validAny = validMask;
+      if (a.numSets > 1) {
+        const int64_t f1 = base1 == 1 ? nv1 : base1 == 2 ? nv2 : nv3;
+        const int64_t self1 = shfl_i64(f1, 0);
+        const bool ok1 =
+          nq >= 0 && (lane == 0 || (10 * f1 > 2 * self1 && 10 * f1 < 25 * self1));
+        const uint32_t valid1 = __ballot_sync(0xffffffffu, ok1);
+        validAny |= valid1;
+        if (si)
+          validMask = valid1;
+      }
     }
   }
 
@@ -351,14 +420,14 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   Quantizer qz[2];
   {
     LayerQp lq;
-    lq.luma = a.qt->layers[a.qpLayer][0];
-    lq.chromaOffset = a.qt->layers[a.qpLayer][1];
-    lq.maxQp = cfg.maxQp;
-    lq.fixedPointQpOffset = cfg.fixedPointQpOffset;
+    lq.luma = my.qt->layers[my.qpLayer][0];
+    lq.chromaOffset = my.qt->layers[my.qpLayer][1];
+    lq.maxQp = my.maxQp;
+    lq.fixedPointQpOffset = my.fixedPointQpOffset;
     int off0 = nodeQp0, off1 = nodeQp1;
-    if (j && a.acLayer < cfg.numAcLayers) {
-      off0 += a.qt->acQps[a.acLayer][j - 1][0];
-      off1 += a.qt->acQps[a.acLayer][j - 1][1];
+    if (j && my.acLayer < my.numAcLayers) {
+      off0 += my.qt->acQps[my.acLayer][j - 1][0];
+      off1 += my.qt->acQps[my.acLayer][j - 1][1];
     }
     make_quantizers(lq, off0, off1, qz);
   }
@@ -425,16 +494,21 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     const int64_t fracMul = ext ? 1 : (int64_t(1) << kFracBits);
     // parent-stage contributions; note which neighbours feed child values
     uint32_t childNb = 0;
-    uint32_t vm = validMask;
+    uint32_t vm = validAny;
     while (vm) {
       const int i = __ffs(vm) - 1;
       vm &= vm - 1;
+      const bool counts = (validMask >> i) & 1;  // for this lane's attribute
       const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
       int64_t mine = shfl_i64(nv0, i);
       if (A > 1) {
         const int64_t m1 = shfl_i64(nv1, i);
         const int64_t m2 = shfl_i64(nv2, i);
         mine = k == 0 ? mine : k == 1 ? m1 : m2;
+      }
+      if (A > 3) {
+        const int64_t m3 = shfl_i64(nv3, i);
+        mine = k == 3 ? m3 : mine;
       }
       const uint32_t mask = uint32_t(neigh_mask(i)) & occ;
       uint32_t cmask = 0;
@@ -445,7 +519,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       }
       if (cmask)
         childNb |= 1u << i;
-      if ((mask >> j) & 1) {
+      if (counts && ((mask >> j) & 1)) {
         if ((cmask >> j) & 1) {
           wsum += cfg.predWeightChild[i - 7];
         } else {
@@ -485,7 +559,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
           const int shift = ii < 9 ? sh : -sh;
           const uint32_t cmask =
             (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
-          if (act && ((cmask >> j) & 1)) {
+          if (act && ((cmask >> j) & 1) && ((validMask >> i) & 1)) {
             const int c = cfirst + __popc(no & ((1u << (j + shift)) - 1));
             ad[u] = &S.rec[size_t(c) * A + k];
             v[u] = ld_rec(ad[u]);
@@ -532,7 +606,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   // the coefficient of this lane before RDOQ (encoder)
   int64_t qcMine = 0;
   if (enc && exists && act)
-    qcMine = qz[k < 1 ? k : 1].quantize(fx_round(buf) << kAttrShift);
+    qcMine = qz[kk < 1 ? kk : 1].quantize(fx_round(buf) << kAttrShift);
 
   bool flagMine = false;
   if (rdoq) {
@@ -544,11 +618,27 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       const int64_t mag = qcMine < 0 ? -qcMine : qcMine;
       stat = (mag > 3 ? 3 : int(mag)) << 16 | lut_log(mag);
     }
-    // sums over the components (lanes 8 and 16 away): every row ends up with them
-    d2 += shfl_xor_i64(d2, 8);
-    d2 += shfl_xor_i64(d2, 16);
-    stat += __shfl_xor_sync(0xffffffffu, stat, 8);
-    stat += __shfl_xor_sync(0xffffffffu, stat, 16);
+    // sums over the components of the lane's attribute: every row ends up with them
+    if (a.numSets == 1) {
+      d2 += shfl_xor_i64(d2, 8);
+      d2 += shfl_xor_i64(d2, 16);
+      stat += __shfl_xor_sync(0xffffffffu, stat, 8);
+      stat += __shfl_xor_sync(0xffffffffu, stat, 16);
+    } else {
+      int64_t d2s = 0;
+      int sts = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int64_t dv = shfl_i64(d2, j + 8 * r);
+        const int sv = __shfl_sync(0xffffffffu, stat, j + 8 * r);
+        if (r >= my.base && r < my.base + my.A) {
+          d2s += dv;
+          sts += sv;
+        }
+      }
+      d2 = d2s;
+      stat = sts;
+    }
     const int aq = stat >> 16, rc = stat & 0xffff;
     int code = kCodeZero;
     if (exists) {
@@ -556,22 +646,21 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         code = kCodeHard;
       } else if (aq > 0) {
         const int64_t l0 = qz[0].scale(1);
-        code = rdoq_code(d2, l0 * l0 * (A == 1 ? 25 : 35), rc);
+        code = rdoq_code(d2, l0 * l0 * (my.A == 1 ? 25 : 35), rc);
       }
     }
     flagMine = code == kCodeRemoved;
     // the block's coefficients by scan position (the rows hold the same values)
-    const uint32_t softM =
-      __reduce_or_sync(0xffffffffu, exists && code >= 3 ? 1u << myPos : 0u);
+    const uint32_t softM = __reduce_or_sync(group, exists && code >= 3 ? 1u << myPos : 0u);
     const uint32_t hardM =
-      __reduce_or_sync(0xffffffffu, exists && code == kCodeHard ? 1u << myPos : 0u);
+      __reduce_or_sync(group, exists && code == kCodeHard ? 1u << myPos : 0u);
     const bool hasS = softM != 0, hasH = hardM != 0;
     unsigned long long codes = 0;
     if (hasS) {
       const uint32_t lo =
-        __reduce_or_sync(0xffffffffu, exists && myPos < 5 ? uint32_t(code) << (6 * myPos) : 0u);
-      const uint32_t hi = __reduce_or_sync(
-        0xffffffffu, exists && myPos >= 5 ? uint32_t(code) << (6 * (myPos - 5)) : 0u);
+        __reduce_or_sync(group, exists && myPos < 5 ? uint32_t(code) << (6 * myPos) : 0u);
+      const uint32_t hi =
+        __reduce_or_sync(group, exists && myPos >= 5 ? uint32_t(code) << (6 * (myPos - 5)) : 0u);
       codes = lo | (unsigned long long)hi << 30;
     }
 
@@ -589,24 +678,34 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         prev = m + 1;
       }
       e += ncoef - prev;
-      if (lane == 0)
-        st_release(&a.words[t + 1], tz_pack(kTzExit, e));
+      if (speaker)
+        st_release(&my.words[t + 1], tz_pack(kTzExit, e));
     } else if (!hasS) {
-      if (lane == 0)
-        st_release(&a.words[t + 1], tz_pack(kTzTransparent, ncoef));
-    } else if (lane == 0) {
-      a.lists[t + 1] = codes;
-      st_release(&a.words[t + 1], tz_pack(kTzClassified, ncoef));
+      if (speaker)
+        st_release(&my.words[t + 1], tz_pack(kTzTransparent, ncoef));
+    } else if (speaker) {
+      my.lists[t + 1] = codes;
+      st_release(&my.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
 
-    // resolve this block's own decisions: only coefficients with a finite
-    // threshold need the run length (everything between them extends it)
-    if (hasS) {
+    // Resolve the block's own decisions, one attribute at a time with all 32
+    // lanes (the look-back is a warp-wide operation): only coefficients with a
+    // finite threshold need the run length, everything between them extends it.
+    uint32_t removed = 0;  // scan positions of this lane's attribute that RDOQ removes
+    for (int q = 0; q < a.numSets; q++) {
+      const AttrSet& sq = a.set[q];
+      const int spk = 8 * sq.base;
+      const uint32_t sM = __shfl_sync(0xffffffffu, softM, spk);
+      if (!sM)
+        continue;
+      const uint32_t hM = __shfl_sync(0xffffffffu, hardM, spk);
+      const unsigned long long cq = (unsigned long long)shfl_i64((int64_t)codes, spk);
       bool linked = true;  // the run still reaches back beyond the block
       int z = 0;           // its length inside the block while linked
       int tl = 0;          // run length since the last reset inside the block
       int prev = 0;
-      uint32_t ev = softM | hardM;
+      uint32_t fl = 0;
+      uint32_t ev = sM | hM;
       while (ev) {
         const int m = __ffs(ev) - 1;
         ev &= ev - 1;
@@ -616,10 +715,10 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
           tl += m - prev;
         prev = m + 1;
         bool f = false;
-        if ((softM >> m) & 1) {
-          const int th = thr_decode(int((codes >> (6 * m)) & 63));
+        if ((sM >> m) & 1) {
+          const int th = thr_decode(int((cq >> (6 * m)) & 63));
           if (linked)
-            f = tz_run_at_least(a, t, th - z);
+            f = tz_run_at_least(sq, a.stageIdx, a.pollNs, t, th - z, lane);
           else
             f = tl >= th;
         }
@@ -633,26 +732,30 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         } else {
           tl = f ? tl + 1 : 0;
         }
-        if (m == myPos)
-          flagMine = f;
+        if (f)
+          fl |= 1u << m;
       }
       tl += ncoef - prev;
-      if (!hasH && lane == 0)
-        st_release(&a.words[t + 1],
+      if (!hM && lane == spk)
+        st_release(&sq.words[t + 1],
                    linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
+      if (q == si)
+        removed = fl;
     }
+    if (hasS && ((softM >> myPos) & 1))
+      flagMine = (removed >> myPos) & 1;
   }
 
   //-- quantise / dequantise (RAHT.cpp:1672-1723)
   if (exists && act) {
-    const Quantizer& qk = qz[k < 1 ? k : 1];
+    const Quantizer& qk = qz[kk < 1 ? kk : 1];
     const int64_t pos = a.coefBase + c0 - (root ? 0 : p) + myPos;
     int64_t qc;
     if (enc) {
       qc = flagMine ? 0 : qcMine;
-      a.coef[k * a.coefStride + pos] = int32_t(qc);
+      my.coef[kk * my.coefStride + pos] = int32_t(qc);
     } else {
-      qc = a.coef[k * a.coefStride + pos];
+      qc = my.coef[kk * my.coefStride + pos];
     }
     pred += fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
   }

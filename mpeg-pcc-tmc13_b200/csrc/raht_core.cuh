@@ -231,7 +231,7 @@ struct MergeFn {
   PCC_HD void operator()(int64_t u) const
   {
     int c0 = C.first[u], c1 = C.first[u + 1];
-    uint32_t at[8][3];
+    uint32_t at[8][4];
     int32_t qp[8][2];
     for (int j = 0; j < 8; j++)
       qp[j][0] = qp[j][1] = 0;
@@ -984,18 +984,26 @@ struct TzCarryFn {
 // last step: duplicate points (RAHT.cpp:1840-1964) and write-back
 // (RAHT.cpp:1967-1975), one thread per leaf.
 
-struct TailFn {
-  RahtConfig cfg;
+// the part of an attribute the tail needs (see AttrSet in raht_block_warp.cuh)
+struct TailSet {
+  int A, base;
+  int maxQp, fixedPointQpOffset;
+  int qpLayer;
   const QpTables* qt;
+  int32_t* coef;
+  int64_t coefStride;
+};
+
+struct TailFn {
+  RahtConfig cfg;          // cfg.A: components of all sets together
+  int numSets;
+  TailSet set[2];
   Stage L;
   const int32_t* attrsIn;  // N*A source values (encoder), Morton order
   const int32_t* dupHf;    // Haar high-pass of the duplicates, or null
   int32_t* attrsOut;       // N*A
-  int32_t* coef;
-  int64_t coefStride;
-  int64_t coefBase;  // coefficients emitted by the stages
-  int qpLayer;
-  int hasStages;     // 0 when all points share one position
+  int64_t coefBase;        // coefficients emitted by the stages
+  int hasStages;           // 0 when all points share one position
 
   PCC_HD void operator()(int64_t ub) const
   {
@@ -1012,64 +1020,68 @@ struct TailFn {
           finish(hasStages ? L.rec[size_t(u) * A + k] : 0);
       return;
     }
-    LayerQp lq;
-    lq.luma = qt->layers[qpLayer][0];
-    lq.chromaOffset = qt->layers[qpLayer][1];
-    lq.maxQp = cfg.maxQp;
-    lq.fixedPointQpOffset = cfg.fixedPointQpOffset;
     int off0 = 0, off1 = 0;
     if (cfg.hasQp) {
       const int32_t* src = hasStages ? L.qpDown : L.qpUp;
       off0 = src[2 * u] >> 4;
       off1 = src[2 * u + 1] >> 4;
     }
-    Quantizer q[2];
-    make_quantizers(lq, off0, off1, q);
     const int64_t sq = int64_t(isqrt64(uint64_t(wt) << (2 * kFracBits)));
-    int64_t pos0 = coefBase + (i0 - u);
-    for (int k = 0; k < A; k++) {
-      const Quantizer& qk = q[k < 1 ? k : 1];
-      int64_t attrSum = fx_from_int(L.attr[size_t(u) * A + k]);
-      int64_t r = hasStages ? L.rec[size_t(u) * A + k] : 0;
-      int64_t recDc = cfg.ext ? r : fx_from_int(r);
-      if (!cfg.haar)
-        recDc = fx_mul(recDc, sq);
-      for (int w = wt - 1; w > 0; w--) {
-        int64_t ca, cb;
-        raht_ab(w, 1, ca, cb);
-        int64_t pos = pos0 + (wt - 1 - w);
-        int64_t qc;
-        if (cfg.isEncoder) {
-          int64_t t0, t1;
-          if (cfg.haar) {
-            // undo the lifting step; the high-pass (right - left) is the
-            // stored difference itself
-            t1 = fx_from_int(dupHf[size_t(i0 + w) * A + k]);
-            attrSum -= t1 >> 1;
+    const int64_t pos0 = coefBase + (i0 - u);
+    for (int si = 0; si < numSets; si++) {
+      const TailSet& ts = set[si];
+      LayerQp lq;
+      lq.luma = ts.qt->layers[ts.qpLayer][0];
+      lq.chromaOffset = ts.qt->layers[ts.qpLayer][1];
+      lq.maxQp = ts.maxQp;
+      lq.fixedPointQpOffset = ts.fixedPointQpOffset;
+      Quantizer q[2];
+      make_quantizers(lq, off0, off1, q);
+      for (int kk = 0; kk < ts.A; kk++) {
+        const int k = ts.base + kk;
+        const Quantizer& qk = q[kk < 1 ? kk : 1];
+        int64_t attrSum = fx_from_int(L.attr[size_t(u) * A + k]);
+        int64_t r = hasStages ? L.rec[size_t(u) * A + k] : 0;
+        int64_t recDc = cfg.ext ? r : fx_from_int(r);
+        if (!cfg.haar)
+          recDc = fx_mul(recDc, sq);
+        for (int w = wt - 1; w > 0; w--) {
+          int64_t ca, cb;
+          raht_ab(w, 1, ca, cb);
+          int64_t pos = pos0 + (wt - 1 - w);
+          int64_t qc;
+          if (cfg.isEncoder) {
+            int64_t t0, t1;
+            if (cfg.haar) {
+              // undo the lifting step; the high-pass (right - left) is the
+              // stored difference itself
+              t1 = fx_from_int(dupHf[size_t(i0 + w) * A + k]);
+              attrSum -= t1 >> 1;
+            } else {
+              t1 = fx_from_int(attrsIn[size_t(i0 + w) * A + k]);
+              attrSum -= t1;
+              t0 = scale_rsqrt(attrSum, w);
+              t1 = fx_mul(t1, ca) - fx_mul(cb, t0);
+            }
+            qc = qk.quantize(fx_round(t1) << kAttrShift);
+            ts.coef[kk * ts.coefStride + pos] = int32_t(qc);
           } else {
-            t1 = fx_from_int(attrsIn[size_t(i0 + w) * A + k]);
-            attrSum -= t1;
-            t0 = scale_rsqrt(attrSum, w);
-            t1 = fx_mul(t1, ca) - fx_mul(cb, t0);
+            qc = ts.coef[kk * ts.coefStride + pos];
           }
-          qc = qk.quantize(fx_round(t1) << kAttrShift);
-          coef[k * coefStride + pos] = int32_t(qc);
-        } else {
-          qc = coef[k * coefStride + pos];
+          int64_t hf = fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
+          int64_t left, right;
+          if (cfg.haar) {
+            left = recDc - ((hf >> (1 + kFracBits)) << kFracBits);
+            right = hf + left;
+          } else {
+            left = fx_mul(recDc, ca) - fx_mul(cb, hf);
+            right = fx_mul(recDc, cb) + fx_mul(ca, hf);
+          }
+          recDc = left;
+          attrsOut[size_t(i0 + w) * A + k] = finish(cfg.ext ? right : fx_round(right));
+          if (w == 1)
+            attrsOut[size_t(i0) * A + k] = finish(cfg.ext ? left : fx_round(left));
         }
-        int64_t hf = fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
-        int64_t left, right;
-        if (cfg.haar) {
-          left = recDc - ((hf >> (1 + kFracBits)) << kFracBits);
-          right = hf + left;
-        } else {
-          left = fx_mul(recDc, ca) - fx_mul(cb, hf);
-          right = fx_mul(recDc, cb) + fx_mul(ca, hf);
-        }
-        recDc = left;
-        attrsOut[size_t(i0 + w) * A + k] = finish(cfg.ext ? right : fx_round(right));
-        if (w == 1)
-          attrsOut[size_t(i0) * A + k] = finish(cfg.ext ? left : fx_round(left));
       }
     }
   }

@@ -129,35 +129,94 @@ make_config(const pccb200_raht_params& pp, const pccb200_qpset& qs, bool forward
   return c;
 }
 
-// keys / attrs / qpo / coef live in executor memory.  attrs: N*A in, out.
-// coef: component k at coef + k*coefStride.  Returns a PCCB200_* status.
+// One attribute of a call: its quantisation parameters and coefficient planes
+// (executor memory; component kk at coef + kk * coefStride).
+struct RahtSetIO {
+  const pccb200_qpset* qs;
+  int A;
+  int32_t* coef;
+  int64_t coefStride;
+};
+
+// what a set needs at run time, for the executor's descent and the tail
+struct RahtSetRt {
+  int A, base;
+  int numLayers, maxQp, fixedPointQpOffset, numAcLayers;
+  const QpTables* qt;
+  int32_t* coef;
+  int64_t coefStride;
+  int* tz;  // zero-run words of the set (layout: tzOff), or null
+};
+
+// keys / attrs / qpo / coefficients live in executor memory.  attrs: N rows of
+// all components of all sets (set 0 first), in and out.  Several sets = several
+// attributes coded on the same positions in one pass: they share the tree and
+// every geometry-only step; that needs the executor's own descent
+// (WaveDescent) and returns PCCB200_ERR_UNSUPPORTED where it cannot be used
+// (the caller then codes the attributes one by one).  Returns a PCCB200_* status.
 template<class Exec>
 int
-raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
-         bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo,
-         int32_t* coef, int64_t coefStride, int A, int N)
+raht_run_sets(Exec& ex, const pccb200_raht_params& pp, int numSets, const RahtSetIO* io,
+              bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo, int N)
 {
-  if (N <= 0 || A < 1 || A > 3 || qs.num_layers < 1
-      || qs.num_layers > PCCB200_MAX_QP_LAYERS
-      || qs.num_ac_coeff_qp_layers > PCCB200_MAX_AC_QP_LAYERS
-      || qs.num_ac_coeff_qp_layers < 0)
+  if (N <= 0 || numSets < 1 || numSets > 2)
+    return PCCB200_ERR_INVALID_ARG;
+  int A = 0;
+  for (int s = 0; s < numSets; s++) {
+    const pccb200_qpset& qs = *io[s].qs;
+    if (io[s].A < 1 || io[s].A > 3 || qs.num_layers < 1 || qs.num_layers > PCCB200_MAX_QP_LAYERS
+        || qs.num_ac_coeff_qp_layers > PCCB200_MAX_AC_QP_LAYERS || qs.num_ac_coeff_qp_layers < 0)
+      return PCCB200_ERR_INVALID_ARG;
+    A += io[s].A;
+  }
+  if (A > 4)
     return PCCB200_ERR_INVALID_ARG;
 
   const bool hasQp = qpo != nullptr;
+  const pccb200_qpset& qs = *io[0].qs;
   RahtConfig cfg = make_config(pp, qs, forward, A, hasQp);
-
-  QpTables hostQt;
-  for (int i = 0; i < PCCB200_MAX_QP_LAYERS; i++) {
-    hostQt.layers[i][0] = qs.layers[i][0];
-    hostQt.layers[i][1] = qs.layers[i][1];
-  }
-  for (int l = 0; l < PCCB200_MAX_AC_QP_LAYERS; l++)
-    for (int c = 0; c < 7; c++) {
-      hostQt.acQps[l][c][0] = qs.ac_coeff_qps[l][c][0];
-      hostQt.acQps[l][c][1] = qs.ac_coeff_qps[l][c][1];
+  if (numSets > 1) {
+    bool ok = N >= 2 && !hasQp;
+    if constexpr (WaveDescent<Exec>::available) {
+      for (int s = 0; s < numSets && ok; s++) {
+        RahtConfig c1 = make_config(pp, *io[s].qs, forward, io[s].A, hasQp);
+        ok = WaveDescent<Exec>::enabled(c1);
+      }
+    } else {
+      ok = false;
     }
-  QpTables* qt = ex.template alloc<QpTables>(1);
-  ex.upload(qt, &hostQt, sizeof(QpTables));
+    if (!ok)
+      return PCCB200_ERR_UNSUPPORTED;
+  }
+
+  RahtSetRt rt[2] = {};
+  for (int s = 0, base = 0; s < numSets; base += io[s].A, s++) {
+    const pccb200_qpset& q = *io[s].qs;
+    QpTables hostQt;
+    for (int i = 0; i < PCCB200_MAX_QP_LAYERS; i++) {
+      hostQt.layers[i][0] = q.layers[i][0];
+      hostQt.layers[i][1] = q.layers[i][1];
+    }
+    for (int l = 0; l < PCCB200_MAX_AC_QP_LAYERS; l++)
+      for (int c = 0; c < 7; c++) {
+        hostQt.acQps[l][c][0] = q.ac_coeff_qps[l][c][0];
+        hostQt.acQps[l][c][1] = q.ac_coeff_qps[l][c][1];
+      }
+    QpTables* dq = ex.template alloc<QpTables>(1);
+    ex.upload(dq, &hostQt, sizeof(QpTables));
+    rt[s].A = io[s].A;
+    rt[s].base = base;
+    rt[s].numLayers = q.num_layers;
+    rt[s].maxQp = q.max_qp;
+    rt[s].fixedPointQpOffset = q.fixed_point_qp_offset;
+    rt[s].numAcLayers = q.num_ac_coeff_qp_layers;
+    rt[s].qt = dq;
+    rt[s].coef = io[s].coef;
+    rt[s].coefStride = io[s].coefStride;
+  }
+  const QpTables* qt = rt[0].qt;
+  int32_t* coef = io[0].coef;
+  const int64_t coefStride = io[0].coefStride;
 
   ex.phase(1);  // tree build
   if (N == 1) {
@@ -225,17 +284,20 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
         tzOff[si] = total;
         total += (si == int(stages.size()) - 1 ? 1 : stages[si + 1].n) + 1;
       }
-      tz = ex.template alloc<int>(size_t(total) + 1);
-      ex.zero(tz, (size_t(total) + 1) * sizeof(int));
+      total++;
+      tz = ex.template alloc<int>(size_t(total) * numSets);
+      ex.zero(tz, size_t(total) * numSets * sizeof(int));
       int init = tz_pack(kTzExit, 0);
-      ex.upload(tz + tzOff[stages.size() - 1], &init, sizeof(int));
+      for (int s = 0; s < numSets; s++) {
+        rt[s].tz = tz + size_t(total) * s;
+        ex.upload(rt[s].tz + tzOff[stages.size() - 1], &init, sizeof(int));
+      }
     }
 
     bool descended = false;
     if constexpr (WaveDescent<Exec>::available) {
-      if (WaveDescent<Exec>::enabled(cfg)) {
-        qpLayer = WaveDescent<Exec>::run(ex, cfg, qt, stages, coef, coefStride, qs.num_layers,
-                                         tz, tzOff);
+      if (numSets > 1 || WaveDescent<Exec>::enabled(cfg)) {
+        WaveDescent<Exec>::run(ex, cfg, numSets, rt, stages, tzOff);
         descended = true;
       }
     }
@@ -280,25 +342,49 @@ raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
   ex.phase(3);
   TailFn tail;
   tail.cfg = cfg;
-  tail.qt = qt;
+  tail.numSets = numSets;
+  for (int s = 0; s < numSets; s++) {
+    TailSet& ts = tail.set[s];
+    ts.A = rt[s].A;
+    ts.base = rt[s].base;
+    ts.maxQp = rt[s].maxQp;
+    ts.fixedPointQpOffset = rt[s].fixedPointQpOffset;
+    // the qp layer of the last stage: one step per stage, saturating
+    const int steps = hasStages ? int(stages.size()) : 0;
+    ts.qpLayer = steps < rt[s].numLayers - 1 ? steps : rt[s].numLayers - 1;
+    if (ts.qpLayer < 0)
+      ts.qpLayer = 0;
+    ts.qt = rt[s].qt;
+    ts.coef = rt[s].coef;
+    ts.coefStride = rt[s].coefStride;
+  }
   tail.L = stages[0];
   tail.attrsIn = attrs;
   tail.dupHf = dupHf;
   tail.attrsOut = attrs;
-  tail.coef = coef;
-  tail.coefStride = coefStride;
   tail.coefBase = hasStages ? nLeaves : 0;
-  tail.qpLayer = qpLayer;
   tail.hasStages = hasStages;
   ex.foreach(nLeaves, tail);
   if (forward && !hasStages) {
     // all points coincide: the reference codes N-1 coefficients and no DC;
     // the last slot of each component is defined as zero here
     int32_t z = 0;
-    for (int k = 0; k < A; k++)
-      ex.upload(coef + k * coefStride + (N - 1), &z, sizeof(int32_t));
+    for (int s = 0; s < numSets; s++)
+      for (int k = 0; k < rt[s].A; k++)
+        ex.upload(rt[s].coef + k * rt[s].coefStride + (N - 1), &z, sizeof(int32_t));
   }
   return PCCB200_OK;
+}
+
+// one attribute (the reference-shaped call)
+template<class Exec>
+int
+raht_run(Exec& ex, const pccb200_raht_params& pp, const pccb200_qpset& qs,
+         bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo,
+         int32_t* coef, int64_t coefStride, int A, int N)
+{
+  RahtSetIO io{&qs, A, coef, coefStride};
+  return raht_run_sets(ex, pp, 1, &io, forward, keys, attrs, qpo, N);
 }
 
 }  // namespace pccb200

@@ -154,11 +154,10 @@ struct WaveDescent<DeviceExec> {
   }
 
   // stages[0] = leaves ... stages.back() = children of the root block.
-  // tz / tzOff: zero-run words as laid out by raht_run.  Returns the qp layer
-  // of the last stage (for the duplicate tail).
-  static int run(DeviceExec& ex, const RahtConfig& cfg, const QpTables* qt,
-                 const std::vector<Stage>& stages, int32_t* coef, int64_t coefStride,
-                 int numLayers, int* tz, const std::vector<int64_t>& tzOff)
+  // rt: the attributes coded in this pass (cfg.A = all their components);
+  // rt[s].tz / tzOff: zero-run words as laid out by raht_run_sets.
+  static void run(DeviceExec& ex, const RahtConfig& cfg, int numSets, const RahtSetRt* rt,
+                  const std::vector<Stage>& stages, const std::vector<int64_t>& tzOff)
   {
     const int top = int(stages.size()) - 1;
     const int A = cfg.A;
@@ -186,7 +185,7 @@ struct WaveDescent<DeviceExec> {
 
     int32_t* wl = ex.alloc<int32_t>(size_t(numRows));
     int32_t* geom = cfg.predictionEnabled ? ex.alloc<int32_t>(size_t(numRows) * kGeomStride) : nullptr;
-    int* cnt = ex.alloc<int>(top + 2);
+    int* cnt = ex.alloc<int>(top + 2);  // [0]: root step, [d]: step d
     // zeroed in one go: the ticket word of every step, the levels
     const size_t zInts = size_t(top + 2) * 2 + (wave ? size_t(numRows) : 0);
     int* zero = ex.alloc<int>(zInts);
@@ -202,6 +201,31 @@ struct WaveDescent<DeviceExec> {
     int64_t abA, abB;
     raht_ab(1, 1, abA, abB);
     std::vector<WarpBlockArgs> args(top + 1);
+    int* cntRoot = cnt;  // cnt[0]: the root step has one block
+    {
+      int one = 1;
+      ex.upload(cntRoot, &one, sizeof(int));
+    }
+    for (int d = 0; d <= top; d++) {
+      WarpBlockArgs& a = args[d];
+      a = WarpBlockArgs{};
+      a.cfg = cfg;
+      a.numSets = numSets;
+      for (int s = 0; s < numSets; s++) {
+        AttrSet& st = a.set[s];
+        st.A = rt[s].A;
+        st.base = rt[s].base;
+        st.maxQp = rt[s].maxQp;
+        st.fixedPointQpOffset = rt[s].fixedPointQpOffset;
+        st.numAcLayers = rt[s].numAcLayers;
+        st.qt = rt[s].qt;
+        st.coef = rt[s].coef;
+        st.coefStride = rt[s].coefStride;
+      }
+      a.ab11a = abA;
+      a.ab11b = abB;
+      a.pollNs = pollNs;
+    }
     for (int d = 1; d <= top; d++) {
       const int si = top - d;
       const Stage& S = stages[si];
@@ -212,21 +236,13 @@ struct WaveDescent<DeviceExec> {
         ex.foreach(nBlocks, prep);
       ex.compact(nBlocks, MultiChildPred{P.first}, WorklistEmit{wl + la.rowOff[d]}, cnt + d);
       WarpBlockArgs& a = args[d];
-      a = WarpBlockArgs{};
-      a.cfg = cfg;
-      a.qt = qt;
       a.S = S;
       a.P = P;
-      a.coef = coef;
-      a.coefStride = coefStride;
       a.coefBase = P.n;
       a.predInLvl = cfg.predictionEnabled;
       a.worklist = wl + la.rowOff[d];
       a.geom = geom ? geom + size_t(la.rowOff[d]) * kGeomStride : nullptr;
       a.count = cnt + d;
-      a.ab11a = abA;
-      a.ab11b = abB;
-      a.pollNs = pollNs;
       if (cfg.predictionEnabled) {
         DeviceExec::Scope sc(ex);
         k_block_geom<<<unsigned((int64_t(nBlocks) * 32 + 255) / 256), 256, 0, ex.stream>>>(a);
@@ -252,7 +268,8 @@ struct WaveDescent<DeviceExec> {
         DeviceExec::Scope sc(ex);
         int64_t blocks = (numRows + 255) / 256;
         const int64_t cap = int64_t(ex.numSMs) * 8;
-        k_block_levels<<<unsigned(blocks > cap ? cap : blocks), 256, 0, ex.stream>>>(la, tickets);
+        k_block_levels<<<unsigned(blocks > cap ? cap : blocks), 256, 0, ex.stream>>>(
+          la, tickets + top + 1);
         g_launchCount++;
       }
       int64_t* kres;
@@ -263,51 +280,48 @@ struct WaveDescent<DeviceExec> {
 
     //-- 4. the stages
     ex.phase(kPhaseBlock);
-    int qpLayer = 0;
-    int acLayer = -1;
+    TzRegion* dRegions[kMaxSets] = {nullptr, nullptr};
+    if (rdoq)
+      for (int s = 0; s < numSets; s++)
+        dRegions[s] = ex.alloc<TzRegion>(kMaxWaveSegs + 2);
     for (int d = 0; d <= top; d++) {
       const int si = top - d;
-      qpLayer = qpLayer + 1 < numLayers ? qpLayer + 1 : numLayers - 1;
-      acLayer++;
       const Stage& S = stages[si];
-      ex.fill(S.rec, 0x80, size_t(S.n) * A * sizeof(int64_t));
-      if (d == 0) {
-        // the root block: the kernel of the Morton-order path, one block
-        BlockFn fn;
-        fn.cfg = cfg;
-        fn.qt = qt;
-        fn.S = S;
-        fn.P = Stage{};
-        fn.P.n = 0;
-        fn.coef = coef;
-        fn.coefStride = coefStride;
-        fn.coefBase = 0;
-        fn.qpLayer = qpLayer;
-        fn.acLayer = acLayer;
-        fn.predInLvl = 0;
-        fn.useFlags = 1;
-        fn.tz = tz ? tz + tzOff[si] : nullptr;
-        ex.block_stage(fn, 1, nullptr);
-        continue;
-      }
-      const Stage& P = stages[si + 1];
-      const int nBlocks = P.n;
-      ex.foreach(nBlocks, PrepFn{cfg, S, P, cfg.predictionEnabled, nullptr, 2});
       WarpBlockArgs& a = args[d];
-      a.qpLayer = qpLayer;
-      a.acLayer = acLayer;
-      TzRegion hr;
-      hr.words = tz ? tz + tzOff[si] : nullptr;
-      hr.lists = tz ? ex.alloc<int>((size_t(nBlocks) + 1) * 2) : nullptr;
-      hr.count = cnt + d;
-      a.stageIdx = ex.numRegions;
-      ex.upload(ex.dRegions + ex.numRegions, &hr, sizeof(TzRegion));
-      ex.numRegions++;
-      a.regions = ex.dRegions;
-      a.words = hr.words;
-      a.lists = reinterpret_cast<unsigned long long*>(hr.lists);
-      a.order = order ? order + la.rowOff[d] : nullptr;
-      a.orderBase = la.rowOff[d];
+      ex.fill(S.rec, 0x80, size_t(S.n) * A * sizeof(int64_t));
+      int nBlocks = 1;
+      if (d == 0) {
+        a.S = S;
+        a.P = Stage{};
+        a.P.n = 0;
+        a.coefBase = 0;
+        a.predInLvl = 0;
+        a.worklist = nullptr;
+        a.geom = nullptr;
+        a.count = cntRoot;
+      } else {
+        const Stage& P = stages[si + 1];
+        nBlocks = P.n;
+        ex.foreach(nBlocks, PrepFn{cfg, S, P, cfg.predictionEnabled, nullptr, 2});
+        a.order = order ? order + la.rowOff[d] : nullptr;
+        a.orderBase = la.rowOff[d];
+      }
+      a.stageIdx = d;
+      for (int s = 0; s < numSets; s++) {
+        AttrSet& st = a.set[s];
+        st.qpLayer = d + 1 < rt[s].numLayers ? d + 1 : rt[s].numLayers - 1;
+        st.acLayer = d;
+        if (rdoq) {
+          TzRegion hr;
+          hr.words = rt[s].tz + tzOff[si];
+          hr.lists = ex.alloc<int>((size_t(nBlocks) + 1) * 2);
+          hr.count = a.count;
+          ex.upload(dRegions[s] + d, &hr, sizeof(TzRegion));
+          st.regions = dRegions[s];
+          st.words = hr.words;
+          st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+        }
+      }
       {
         DeviceExec::Scope sc(ex);
         k_block_warp<<<unsigned(ex.block_grid(nBlocks)), kWarpBlockThreads, 0, ex.stream>>>(
@@ -316,7 +330,6 @@ struct WaveDescent<DeviceExec> {
       }
       PCC_CUDA_CHECK(cudaGetLastError());
     }
-    return qpLayer;
   }
 };
 

@@ -226,6 +226,66 @@ def attr_raht_decode(params, qpset, xyz, coeffs, bitdepth=8, qpoffs=None):
     return attrs
 
 
+def _multi_args(qpsets, arrays_attrs, arrays_coef, bitdepths):
+    k = len(qpsets)
+    QP = C.POINTER(QpSet) * k
+    IP = C.POINTER(C.c_int32) * k
+    qp = QP(*[C.pointer(q) for q in qpsets])
+    at = IP(*[_p(a, C.c_int32) for a in arrays_attrs])
+    co = IP(*[_p(c, C.c_int32) for c in arrays_coef])
+    na = (C.c_int32 * k)(*[int(a.shape[1]) for a in arrays_attrs])
+    bd = (C.c_int32 * k)(*bitdepths)
+    return qp, at, co, na, bd
+
+
+def attr_raht_encode_multi_into(params, qpsets, xyz, attrs_inout, coeffs_out, bitdepths=None):
+    """Several attributes of one slice in one pass (zero-copy form).
+    attrs_inout[s]: [N, A_s] int32 (overwritten with the reconstruction),
+    coeffs_out[s]: [A_s, N] int32."""
+    k = len(qpsets)
+    bitdepths = bitdepths or [8] * k
+    n = attrs_inout[0].shape[0]
+    qp, at, co, na, bd = _multi_args(qpsets, attrs_inout, coeffs_out, bitdepths)
+    _check(lib().pccb200_attr_raht_encode_multi(
+        C.byref(params), C.c_int32(k), qp, _p(xyz, C.c_int32), at, na, bd, C.c_int32(n), co))
+
+
+def attr_raht_encode_multi(params, qpsets, xyz, attrs, bitdepths=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    a = [np.ascontiguousarray(x, dtype=np.int32).copy() for x in attrs]
+    c = [np.empty((x.shape[1], x.shape[0]), dtype=np.int32) for x in a]
+    attr_raht_encode_multi_into(params, qpsets, xyz, a, c, bitdepths)
+    return a, c
+
+
+def attr_raht_decode_multi(params, qpsets, xyz, coeffs, bitdepths=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+    k = len(qpsets)
+    bitdepths = bitdepths or [8] * k
+    c = [np.ascontiguousarray(x, dtype=np.int32) for x in coeffs]
+    a = [np.empty((x.shape[1], x.shape[0]), dtype=np.int32) for x in c]
+    n = a[0].shape[0]
+    qp, at, co, na, bd = _multi_args(qpsets, a, c, bitdepths)
+    _check(lib().pccb200_attr_raht_decode_multi(
+        C.byref(params), C.c_int32(k), qp, _p(xyz, C.c_int32), at, na, bd, C.c_int32(n), co))
+    return a
+
+
+def attr_raht_encode_multi_dev(params, qpsets, d_xyz, d_attrs, d_coefs, n, num_attrs, bitdepths=None):
+    """device pointers (ints) for xyz, each attribute array and each coefficient array"""
+    k = len(qpsets)
+    bitdepths = bitdepths or [8] * k
+    QP = C.POINTER(QpSet) * k
+    VP = C.c_void_p * k
+    qp = QP(*[C.pointer(q) for q in qpsets])
+    at = VP(*d_attrs)
+    co = VP(*d_coefs)
+    na = (C.c_int32 * k)(*num_attrs)
+    bd = (C.c_int32 * k)(*bitdepths)
+    _check(lib().pccb200_attr_raht_encode_multi_dev(
+        C.byref(params), C.c_int32(k), qp, C.c_void_p(d_xyz), at, na, bd, C.c_int32(n), co))
+
+
 def quant_weights(preds, num_points_in_lod):
     preds = np.ascontiguousarray(preds, dtype=PREDICTOR_DTYPE)
     npl = np.ascontiguousarray(num_points_in_lod, dtype=np.uint32)

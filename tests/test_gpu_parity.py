@@ -195,6 +195,49 @@ def test_full_size_vs_oracle(b200, tex):
         assert np.array_equal(b200.attr_raht_decode(p, q, xyz, coef), exp)
 
 
+@pytest.mark.parametrize("case", ["lidar", "shell_dups", "haar", "noext_nosub", "layers", "aclayers"])
+def test_multi_attribute_pass(b200, case):
+    """Colour + reflectance of a slice in ONE pass (shared sort, tree, geometry,
+    dependency chain; own QpSet / coefficients / zero-run state per attribute)
+    against the oracle run once per attribute, encoder and decoder."""
+    from pcc_attr_b200.synth import texture
+
+    kw, q1kw, q2kw = {}, dict(qp=34), dict(qp=28, chroma_offset=0)
+    if case == "lidar":
+        xyz, rgb = cloud_lidar(300000, seed=5)
+        rgb = texture(rgb, 20, 3)
+    elif case == "shell_dups":
+        xyz, rgb = cloud_shell(60000, bits=9, seed=8, dups=True)
+    else:
+        xyz, rgb = cloud_shell(50000, bits=9, seed=9)
+        rgb = texture(rgb, 24, 4)
+    if case == "haar":
+        kw = dict(haar=1)
+    elif case == "noext_nosub":
+        kw = dict(ext=0, subnode=0)
+    elif case == "layers":
+        q1kw = dict(qp=30, layers=[(30, -2), (34, 0), (38, 2)])
+        q2kw = dict(qp=22)
+    elif case == "aclayers":  # no fused path in the encoder: coded one by one internally
+        q1kw = dict(qp=34, ac_qps=[[(c % 3 - 1, (c + 1) % 3 - 1) for c in range(7)], [(1, 0)] * 7])
+    refl = texture(((rgb[:, :1] * 2 + rgb[:, 2:3]) // 3).astype(np.int32), 12, 6)
+    params = make_params(search_range=500, **kw)
+    qs = [make_qpset(**q1kw), make_qpset(**q2kw)]
+    p = b200.RahtParams.from_buffer_copy(bytes(params))
+    q = [b200.QpSet.from_buffer_copy(bytes(x)) for x in qs]
+    recs, coefs = b200.attr_raht_encode_multi(p, q, xyz, [rgb, refl])
+    for s, attrs in enumerate((rgb, refl)):
+        mort, a_s, order = sort_cloud(xyz, attrs)
+        orec, ocoef = oracle_raht(1, params, qs[s], mort, a_s)
+        exp = np.empty_like(orec)
+        exp[order] = np.clip(orec, 0, 255)
+        assert np.array_equal(coefs[s], ocoef), (case, s)
+        assert np.array_equal(recs[s], exp), (case, s)
+    dec = b200.attr_raht_decode_multi(p, q, xyz, coefs)
+    for s in range(2):
+        assert np.array_equal(dec[s], recs[s]), (case, s)
+
+
 @pytest.mark.parametrize("a", [1, 3])
 def test_lifting_vs_oracle(b200, a):
     """quantisation weights and forward / inverse lifting (64-bit atomics per
