@@ -33,9 +33,25 @@ def write_ply(path, xyz, rgb):
             f.write("%d %d %d %d %d %d\n" % (p[0], p[1], p[2], c[0], c[1], c[2]))
 
 
-def encode(binary, ply, out_bin, out_rec, qp=34):
+# cfg/octree-liftt-ctc-lossless-geom-lossy-attrs.yaml (transformType 2) and
+# cfg/octree-predt-ctc-lossless-geom-nearlossless-attrs.yaml (transformType 1), colour
+def lod_flags(qp=34, transform_type=2, decimator=0, lods=10):
+    f = [x for x in enc_flags(qp, transform_type) if not x.startswith("--rahtPredictionSearchRange")
+         and not x.startswith("--qpChromaOffset")]
+    i = f.index(f"--qp={qp}")
+    extra = ["--numberOfNearestNeighborsInPrediction=3", f"--levelOfDetailCount={lods}",
+             f"--lodDecimator={decimator}", "--adaptivePredictionThreshold=64", "--qpChromaOffset=0"]
+    if decimator:
+        extra += ["--lodSamplingPeriod=4", "--lod_neigh_bias=1,1,1"]
+    if transform_type == 1:
+        extra += ["--intraLodPredictionSkipLayers=0", "--interComponentPredictionEnabled=0",
+                  "--predWeightBlending=1"]
+    return f[:i] + extra + f[i:]
+
+
+def encode(binary, ply, out_bin, out_rec, qp=34, flags=None):
     cmd = [binary, f"--uncompressedDataPath={ply}", f"--compressedStreamPath={out_bin}",
-           f"--reconstructedDataPath={out_rec}"] + enc_flags(qp)
+           f"--reconstructedDataPath={out_rec}"] + (flags if flags is not None else enc_flags(qp))
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return r.returncode, r.stdout
 

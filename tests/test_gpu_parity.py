@@ -334,6 +334,84 @@ def test_whole_codec_bitstream(b200, tmp_path):
         assert md5(d_ref) == md5(d_b200) == md5(out["ref"][1])
 
 
+@pytest.mark.parametrize("tt,decimator", [(2, 0), (2, 1), (2, 2), (1, 0)])
+def test_whole_codec_bitstream_lifting(b200, tmp_path, tt, decimator):
+    """The reference's tmc3 executable with AttributeLods::generate replaced by
+    the drop-in translation unit (host/lod_dropin.cpp: the level-of-detail build
+    runs on the GPU, the reference's own lifting / predicting loops and entropy
+    coder run on its predictors) produces the same bitstream and reconstruction
+    as the unmodified executable, and decodes the reference's bitstream
+    identically (transformType 2 = lifting, 1 = predicting)."""
+    import hashlib
+
+    import codec_harness as ch
+
+    if not (os.path.exists(ch.REF_BIN) and os.path.exists(ch.B200_BIN)):
+        pytest.skip("oracle/_ref/tmc3_{ref,b200} not built (make -C oracle codec)")
+    xyz, rgb = cloud_shell(100000, bits=10, seed=12)
+    ply = str(tmp_path / "in.ply")
+    ch.write_ply(ply, xyz, rgb)
+
+    def md5(p):
+        return hashlib.md5(open(p, "rb").read()).hexdigest()
+
+    flags = ch.lod_flags(qp=34, transform_type=tt, decimator=decimator)
+    out = {}
+    for name, binary in (("ref", ch.REF_BIN), ("b200", ch.B200_BIN)):
+        b, r = str(tmp_path / f"{name}.bin"), str(tmp_path / f"{name}_rec.ply")
+        rc, log = ch.encode(binary, ply, b, r, flags=flags)
+        assert rc == 0, log[-2000:]
+        out[name] = (b, r)
+    assert md5(out["ref"][0]) == md5(out["b200"][0]), "bitstreams differ"
+    assert md5(out["ref"][1]) == md5(out["b200"][1]), "encoder reconstructions differ"
+    d_ref, d_b200 = str(tmp_path / "dref.ply"), str(tmp_path / "db200.ply")
+    assert ch.decode(ch.REF_BIN, out["ref"][0], d_ref)[0] == 0
+    rc, log = ch.decode(ch.B200_BIN, out["ref"][0], d_b200)
+    assert rc == 0, log[-2000:]
+    assert md5(d_ref) == md5(d_b200) == md5(out["ref"][1])
+
+
+def test_lod_handle_reuse(b200):
+    """Levels of detail built once per slice and used by the colour and the
+    reflectance call (AttributeEncoder::_lods): same results as the calls that
+    rebuild them; the reuse rule follows AttributeLods::isReusable."""
+    import ctypes as C
+
+    xyz, rgb = cloud_shell(80000, bits=10, seed=21)
+    refl = ((rgb[:, :1] + rgb[:, 1:2]) // 2).astype(np.int32)
+    lp = _as_lod(b200, make_lod_params(levels=10))
+    q = b200.QpSet.from_buffer_copy(bytes(make_qpset(qp=34, fixed_point_qp_offset=24)))
+    h = C.c_void_p()
+    L = b200.lib()
+    x = np.ascontiguousarray(xyz, dtype=np.int32)
+    assert L.pccb200_lod_create(C.byref(lp), x.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(len(x)),
+                                C.byref(h)) == 0
+    try:
+        assert L.pccb200_lod_reusable(h, C.byref(lp)) == 1
+        lp2 = _as_lod(b200, make_lod_params(levels=10, k=2))
+        assert L.pccb200_lod_reusable(h, C.byref(lp2)) == 0
+        for attrs, lcp in ((rgb, 1), (refl, 0)):
+            val0, rec0, lcp0 = b200.attr_lift_encode(lp, q, xyz, attrs, lcp_enabled=lcp)
+            a = np.ascontiguousarray(attrs, dtype=np.int32).copy()
+            vals = np.empty_like(a)
+            lc = np.zeros(33, dtype=np.int8)
+            rc = L.pccb200_attr_lift_encode_lod(
+                h, C.byref(q), C.c_int32(lcp), None, a.ctypes.data_as(C.POINTER(C.c_int32)),
+                C.c_int32(a.shape[1]), C.c_int32(8), vals.ctypes.data_as(C.POINTER(C.c_int32)),
+                lc.ctypes.data_as(C.POINTER(C.c_int8)))
+            assert rc == 0
+            assert np.array_equal(a, rec0) and np.array_equal(vals, val0)
+            assert np.array_equal(lc[:10], np.asarray(lcp0)[:10])
+            dec = np.empty_like(a)
+            rc = L.pccb200_attr_lift_decode_lod(
+                h, C.byref(q), C.c_int32(lcp), None, dec.ctypes.data_as(C.POINTER(C.c_int32)),
+                C.c_int32(a.shape[1]), C.c_int32(8), vals.ctypes.data_as(C.POINTER(C.c_int32)),
+                lc.ctypes.data_as(C.POINTER(C.c_int8)))
+            assert rc == 0 and np.array_equal(dec, a)
+    finally:
+        L.pccb200_lod_destroy(h)
+
+
 def _as_lod(pb, lp):
     return pb.LodParams.from_buffer_copy(bytes(lp))
 

@@ -55,9 +55,30 @@ def run(label, params, a, attrs, decode=False):
           flush=True)
 
 
+def run_multi(label, decode=False):
+    recs, coefs = pb.attr_raht_encode_multi(p, [q, q], xyz, [rgb, refl])
+    fn = (lambda: pb.attr_raht_decode_multi(p, [q, q], xyz, coefs)) if decode else \
+        (lambda: pb.attr_raht_encode_multi(p, [q, q], xyz, [rgb, refl]))
+    fn()
+    pb.profile_reset()
+    pb.profile_enable(True)
+    t0 = time.perf_counter()
+    fn()
+    t1 = time.perf_counter()
+    pb.profile_enable(False)
+    pr = pb.profile_read()
+    print(f"{label:24s} A=3+1 wall {1e3*(t1-t0):7.1f} ms  block {pr['block_transform'][0]:7.2f} ms "
+          f"({pr['block_transform'][1]:3d}) geom {pr['block_geometry'][0]:5.2f} ({pr['block_geometry'][1]:3d}) "
+          f"sched {pr['block_schedule'][0]:5.2f} ({pr['block_schedule'][1]:3d}) sort {pr['sort'][0]:.2f} "
+          f"tree {pr['tree_build'][0]:.2f} tail {pr['tail'][0]:.2f} gather {pr['gather_scatter'][0]:.2f}",
+          flush=True)
+
+
 pn = pb.RahtParams.from_buffer_copy(bytes(p)); pn.prediction_enabled = 0
 ps = pb.RahtParams.from_buffer_copy(bytes(p)); ps.subnode_prediction_enabled = 0
 full = os.environ.get("QP_FULL", "1") != "0"
+run_multi("enc multi")
+run_multi("dec multi", decode=True)
 for a, attrs in ((3, rgb), (1, refl)):
     run("enc default", p, a, attrs)
     run("dec default", p, a, attrs, decode=True)
