@@ -387,6 +387,23 @@ int pccb200_attr_lift_decode(const pccb200_lod_params* lod,
                              int32_t bitdepth, const int32_t* values_in,
                              const int8_t* lcp_coeffs);
 
+/* The slices of a frame, each with its own levels of detail, each on its own
+ * lane (they overlap on the device).  Slice s owns points
+ * [slice_offsets[s], slice_offsets[s+1]) of every per-point array and row s
+ * (PCCB200_MAX_LODS entries) of the lcp array. */
+int pccb200_attr_lift_encode_slices(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                    int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                    const int32_t* xyz, int32_t* attrs_inout,
+                                    int32_t num_attrs, int32_t bitdepth,
+                                    const int64_t* slice_offsets, int32_t num_slices,
+                                    int32_t* values_out, int8_t* lcp_coeffs_out);
+int pccb200_attr_lift_decode_slices(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                    int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                    const int32_t* xyz, int32_t* attrs_out, int32_t num_attrs,
+                                    int32_t bitdepth, const int64_t* slice_offsets,
+                                    int32_t num_slices, const int32_t* values_in,
+                                    const int8_t* lcp_coeffs);
+
 /* Levels of detail kept across the attributes of a slice ------------------------
  *
  * AttributeEncoder / AttributeDecoder keep the LoDs of a slice

@@ -1198,6 +1198,55 @@ pccb200_attr_lift_decode(const pccb200_lod_params* lod, const pccb200_qpset* qps
                           const_cast<int8_t*>(lcp_coeffs));
 }
 
+// Slices of a frame (tmc3/encoder.cpp:545-568): each with its own levels of
+// detail, each on its own lane.  lcp: num_slices rows of PCCB200_MAX_LODS.
+static int
+attr_lift_slices(bool forward, const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                 int32_t lcpEnabled, const int32_t* qpo, const int32_t* xyz, int32_t* attrs,
+                 int32_t A, int32_t bitdepth, const int64_t* sliceOffsets, int32_t numSlices,
+                 int32_t* values, int8_t* lcp)
+{
+  if (!sliceOffsets || numSlices <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  for (int s = 0; s < numSlices; s++) {
+    const int64_t len = sliceOffsets[s + 1] - sliceOffsets[s];
+    if (len <= 0 || len > INT32_MAX)
+      return fail(PCCB200_ERR_INVALID_ARG, "empty or oversized slice");
+  }
+  return parallel_for(numSlices, kMaxSliceThreads, [&](int s) -> int {
+    const int64_t o = sliceOffsets[s];
+    return attr_lift_common(forward, lod, qpset, lcpEnabled, qpo ? qpo + 2 * o : nullptr,
+                            xyz + 3 * o, attrs + o * A, A, int32_t(sliceOffsets[s + 1] - o),
+                            bitdepth, values + o * A,
+                            lcp ? lcp + size_t(s) * PCCB200_MAX_LODS : nullptr);
+  });
+}
+
+int
+pccb200_attr_lift_encode_slices(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                const int32_t* xyz, int32_t* attrs_inout, int32_t num_attrs,
+                                int32_t bitdepth, const int64_t* slice_offsets,
+                                int32_t num_slices, int32_t* values_out, int8_t* lcp_coeffs_out)
+{
+  return attr_lift_slices(true, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_inout,
+                          num_attrs, bitdepth, slice_offsets, num_slices, values_out,
+                          lcp_coeffs_out);
+}
+
+int
+pccb200_attr_lift_decode_slices(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                int32_t lcp_enabled, const int32_t* point_qp_offsets,
+                                const int32_t* xyz, int32_t* attrs_out, int32_t num_attrs,
+                                int32_t bitdepth, const int64_t* slice_offsets,
+                                int32_t num_slices, const int32_t* values_in,
+                                const int8_t* lcp_coeffs)
+{
+  return attr_lift_slices(false, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_out,
+                          num_attrs, bitdepth, slice_offsets, num_slices,
+                          const_cast<int32_t*>(values_in), const_cast<int8_t*>(lcp_coeffs));
+}
+
 //----------------------------------------------------------------------------
 // spherical coordinates (spherical.cuh)
 
