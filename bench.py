@@ -752,11 +752,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lifting", action="store_true", help="skip the extra lifting-path measurement")
     ap.add_argument("--no-smooth", action="store_true", help="skip the extra smooth-frame measurement")
+    ap.add_argument("--workload", default="raht1m", choices=["raht1m", "predlift3m", "lift10m", "raht30m"],
+                    help="raht1m = BASELINE configs[1] (the headline); the others are configs[2]-[4] "
+                         "(bench_workloads.py)")
+    ap.add_argument("--points", type=int, default=0, help="override the point count of --workload")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP,
                     help="independent frames in flight per GPU per step (intra coding: frames "
                          "are independent work units)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload != "raht1m":
+        import bench_workloads
+
+        if args.impl == "reference":
+            bench_workloads.run_reference(args, sys.modules[__name__])
+        else:
+            bench_workloads.run(args, sys.modules[__name__])
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -295,15 +295,22 @@ struct Profiler {
   }
   void resolve()
   {
+    static const bool debug = getenv("PCCB200_DEBUG") != nullptr;
+    if (debug && !pending.empty())
+      fprintf(stderr, "[pccb200] block-transform launches (ms):");
     for (auto& p : pending) {
       float t = 0;
       if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) {
         ms[p.phase] += t;
         launches[p.phase]++;
+        if (debug && p.phase == 2)
+          fprintf(stderr, " %.3f", t);
       }
       pool.push_back(p.a);
       pool.push_back(p.b);
     }
+    if (debug && !pending.empty())
+      fprintf(stderr, "\n");
     pending.clear();
   }
 };

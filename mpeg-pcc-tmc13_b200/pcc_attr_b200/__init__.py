@@ -78,18 +78,23 @@ PREDICTOR_DTYPE = np.dtype([("neighbor_count", "<u4"), ("predictor_index", "<u4"
                             ("weight", "<u4", 3)])
 
 EXPORTS = [
-    "pccb200_raht_params_default", "pccb200_raht_set_prediction_weights",
-    "pccb200_abi_version", "pccb200_set_device", "pccb200_last_error",
-    "pccb200_kernel_launch_count", "pccb200_morton_sort", "pccb200_raht_forward",
-    "pccb200_raht_inverse", "pccb200_attr_raht_encode", "pccb200_attr_raht_decode",
-    "pccb200_attr_raht_encode_slices", "pccb200_quant_weights",
-    "pccb200_lift_forward", "pccb200_lift_inverse", "pccb200_lod_build", "pccb200_lift_quantize", "pccb200_lift_dequantize",
-    "pccb200_attr_lift_encode", "pccb200_attr_lift_decode", "pccb200_time_begin", "pccb200_time_end",
-    "pccb200_attr_raht_encode_slices_dev", "pccb200_attr_raht_decode_slices_dev",
-    "pccb200_profile_enable", "pccb200_profile_reset", "pccb200_profile_read",
-    "pccb200_xyz_to_rpl", "pccb200_offset_and_scale", "pccb200_attr_spherical_positions",
-    "pccb200_coeff_symbols", "pccb200_attr_raht_encode_symbols", "pccb200_estimate_dist2",
-    "pccb200_quant_weights_fixed", "pccb200_quant_weights_scalable",
+    "pccb200_abi_version", "pccb200_attr_lift_decode", "pccb200_attr_lift_decode_lod",
+    "pccb200_attr_lift_decode_slices", "pccb200_attr_lift_encode", "pccb200_attr_lift_encode_lod",
+    "pccb200_attr_lift_encode_slices", "pccb200_attr_raht_decode",
+    "pccb200_attr_raht_decode_multi", "pccb200_attr_raht_decode_multi_dev",
+    "pccb200_attr_raht_decode_slices_dev", "pccb200_attr_raht_encode",
+    "pccb200_attr_raht_encode_multi", "pccb200_attr_raht_encode_multi_dev",
+    "pccb200_attr_raht_encode_slices", "pccb200_attr_raht_encode_slices_dev",
+    "pccb200_attr_raht_encode_symbols", "pccb200_attr_spherical_positions",
+    "pccb200_coeff_symbols", "pccb200_estimate_dist2", "pccb200_kernel_launch_count",
+    "pccb200_last_error", "pccb200_lift_dequantize", "pccb200_lift_forward",
+    "pccb200_lift_inverse", "pccb200_lift_quantize", "pccb200_lod_build", "pccb200_lod_create",
+    "pccb200_lod_destroy", "pccb200_lod_info", "pccb200_lod_reusable", "pccb200_morton_sort",
+    "pccb200_offset_and_scale", "pccb200_profile_enable", "pccb200_profile_read",
+    "pccb200_profile_reset", "pccb200_quant_weights", "pccb200_quant_weights_fixed",
+    "pccb200_quant_weights_scalable", "pccb200_raht_forward", "pccb200_raht_inverse",
+    "pccb200_raht_params_default", "pccb200_raht_set_prediction_weights", "pccb200_set_device",
+    "pccb200_time_begin", "pccb200_time_end", "pccb200_xyz_to_rpl",
 ]
 NUM_PHASES = 8
 PHASE_NAMES = ["sort", "tree_build", "block_transform", "tail", "gather_scatter", "lifting",

@@ -101,6 +101,34 @@ def cloud_lidar(n=1000000, seed=2, a=3, scale=0.25, lasers=64):
     return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
 
 
+def cloud_terrain(n, seed=7, a=3):
+    """Dense voxelised surface with millions of points (configs[2]-[4] sizes):
+    a height field over a square grid, one voxel per (x, y), so the points are
+    unique by construction (no 30M-point np.unique)."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(np.sqrt(n)))
+    x, y = np.meshgrid(np.arange(side, dtype=np.int32), np.arange(side, dtype=np.int32), indexing="ij")
+    x, y = x.ravel()[:n], y.ravel()[:n]
+    fx, fy = x / float(side), y / float(side)
+    h = (0.25 * np.sin(7.0 * fx + 0.5) * np.cos(5.0 * fy) + 0.12 * np.sin(23.0 * fx * fy + 1.0)
+         + 0.05 * np.cos(61.0 * fy)) * side
+    z = np.rint(h - h.min()).astype(np.int32)
+    xyz = np.stack([x, y, z], axis=1).astype(np.int32)
+    xyz = xyz[rng.permutation(n)]
+    return np.ascontiguousarray(xyz), _smooth_attr(xyz, rng, a)
+
+
+def morton_slices(xyz, attrs_list, max_points):
+    """Partition a cloud into contiguous Morton ranges of at most max_points
+    (octree-aligned slices, tmc3/TMC3.cpp:781-810 level limit): returns the
+    arrays reordered slice by slice and the slice offsets."""
+    order = np.argsort(np_morton(xyz), kind="stable")
+    n = xyz.shape[0]
+    k = (n + max_points - 1) // max_points
+    offs = np.linspace(0, n, k + 1).astype(np.int64)
+    return (np.ascontiguousarray(xyz[order]), [np.ascontiguousarray(a[order]) for a in attrs_list], offs)
+
+
 def cloud_random(n, bits, seed, a=3, dup_frac=0.0, bitdepth=8):
     """Uniform random voxels (worst case for neighbourhood structure)."""
     rng = np.random.default_rng(seed)
