@@ -221,165 +221,67 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 // another block's own answer (whatever a block publishes later is consistent
 // with its list, so the answer does not depend on when a word is read).
 //
-// Called by all 32 lanes: up to two attributes (kMaxSets) ask at once, each
-// about its own zero-run stream; lanes [16 q, 16 q + 16) fetch the state
-// words (and lists) of 16 predecessors of stream q per round trip, then every
-// lane walks over them in registers.  The first batch is normally handed in:
-// it was fetched when the block started (wPre / lPre, TzPrefetch), long before
-// the block's own classification was known, so that on a chain of adjacent
-// blocks -- where the predecessor's reconstruction arrives last and everything
-// after it is on the critical path of the whole stage -- the look-back costs
-// no memory round trip.  Stale entries are as good as fresh ones (a block's
-// list stays consistent with whatever it publishes later); entries that were
-// still empty are fetched again.
-//
-// The walk keeps d = positions that still have to be verified.  A block of
-// v coefficients with the soft ones at offsets k (from its end) turns d into
-// R - v, R = the reach of the chain "k <= R  =>  R = max(R, k + threshold_k)"
-// started at R = d; R <= v ends the walk with "yes".
-struct TzPrefetch {
-  int w;                  // state word of predecessor t - 1 - (lane & 15) of stream lane >> 4
-  unsigned long long l;   // its list, if classified
-};
-
-__device__ __forceinline__ uint32_t
-tz_soft_offsets(unsigned long long L, int v)
+// Every lane walks the stream of its own attribute (the lanes of an
+// attribute read the same words and agree; the attributes of a pass walk side
+// by side in the same instruction stream).  Two warp-cooperative variants --
+// 32 predecessors fetched per round trip, and two streams at once with the
+// first batch fetched when the block starts -- were measured slower (345 and
+// 392 ms against 304 ms on the textured frame): what bounds a stage there is
+// not the memory latency of the walk but the instruction issue the waiting
+// warps take from the one warp that can make progress, and a heavier loop
+// around the poll makes every waiting warp more expensive.
+__device__ __forceinline__ bool
+tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, int need,
+                const int wPre1, const int wPre2)
 {
-  uint32_t sm = 0;
-#pragma unroll
-  for (int k = 1; k <= 8; k++)
-    if (k <= v && ((L >> (6 * (v - k))) & 63) >= 3)
-      sm |= 1u << (k - 1);
-  return sm;
-}
-
-__device__ __forceinline__ TzPrefetch
-tz_prefetch_words(const WarpBlockArgs& a, const int t, const int lane)
-{
-  TzPrefetch pf;
-  pf.w = 0;
-  pf.l = 0;
-  const int q = lane >> 4;
-  const int idx = t - 1 - (lane & 15);
-  if (q < a.numSets && idx >= 0)
-    pf.w = ld_acquire(&a.set[q].words[idx + 1]);
-  return pf;
-}
-
-__device__ __forceinline__ void
-tz_prefetch_lists(const WarpBlockArgs& a, const int t, const int lane, TzPrefetch& pf)
-{
-  if (tz_status(pf.w) == kTzClassified)
-    pf.l = a.set[lane >> 4].lists[t - (lane & 15)];
-}
-
-// need[q] > 0: stream q asks "is the run before block t at least need[q]
-// long?"; the answer comes back in yes[q].  need[q] <= 0: stream q does not ask.
-__device__ __forceinline__ void
-tz_runs_at_least(const WarpBlockArgs& a, const int t, const int need0, const int need1,
-                 const TzPrefetch& pf, const int lane, bool& yes0, bool& yes1)
-{
-  const int q = lane >> 4;   // the stream this lane fetches for
-  const int hl = lane & 15;
-  int d[2] = {need0, need1};
-  bool open[2] = {need0 > 0, need1 > 0};
-  bool ans[2] = {false, false};
-  int u[2] = {t - 1, t - 1};
-  int sg[2] = {a.stageIdx, a.stageIdx};
-  const int* words = a.set[q < a.numSets ? q : 0].words;
-  const unsigned long long* lists = a.set[q < a.numSets ? q : 0].lists;
-  bool first = true;
-  while (open[0] || open[1]) {
-    // a stream that has walked back to the start of its stage goes on with the
-    // previous one
-#pragma unroll
-    for (int r = 0; r < 2; r++)
-      if (open[r] && u[r] < 0) {
-        if (--sg[r] < 0) {
-          open[r] = false;  // start of the call: the counter starts at 0 (and d > 0)
-          ans[r] = false;
-        } else {
-          const TzRegion rg = a.set[r].regions[sg[r]];
-          if (q == r) {
-            words = rg.words;
-            lists = reinterpret_cast<const unsigned long long*>(rg.lists);
-          }
-          u[r] = *rg.count - 1;
-        }
-      }
-    if (!(open[0] || open[1]))
-      break;
-    const bool mine = q == 0 ? open[0] : open[1];
-    const int idx = (q == 0 ? u[0] : u[1]) - hl;
-    int w = 0;
-    unsigned long long L = 0;
-    if (mine && idx >= 0) {
-      if (first && tz_status(pf.w) != kTzNone) {
-        w = pf.w;
-        L = pf.l;
-        if (tz_status(w) == kTzClassified && L == 0)
-          L = lists[idx + 1];
-      } else {
-        w = ld_acquire(&words[idx + 1]);
-        if (tz_status(w) == kTzClassified)
-          L = lists[idx + 1];
-      }
-    }
-    first = false;
-    const uint32_t stop = __ballot_sync(0xffffffffu, !mine || idx < 0 || tz_status(w) == kTzNone);
-    int usable[2];
-    usable[0] = (stop & 0xffffu) ? __ffs(stop & 0xffffu) - 1 : 16;
-    usable[1] = (stop >> 16) ? __ffs(stop >> 16) - 1 : 16;
-    if ((!open[0] || usable[0] == 0) && (!open[1] || usable[1] == 0)) {
-      __nanosleep(a.pollNs);  // the nearest predecessor has not published anything yet
+  if (need <= 0)
+    return true;
+  int req = need;  // positions 1..req behind the block must not reset the run
+  int acc = 0;     // positions already verified
+  int s = stageIdx;
+  const int* words = st.words;
+  const unsigned long long* lists = st.lists;
+  int u = t - 1;
+  for (;;) {
+    if (u < 0) {
+      if (--s < 0)
+        return acc >= req;  // start of the call: the counter starts at 0
+      const TzRegion rg = st.regions[s];
+      words = rg.words;
+      lists = reinterpret_cast<const unsigned long long*>(rg.lists);
+      u = *rg.count - 1;
       continue;
     }
-    const uint32_t sm = tz_status(w) == kTzClassified ? tz_soft_offsets(L, tz_value(w)) : 0u;
-    for (int i = 0; i < 16; i++) {
-      bool any = false;
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        if (!open[r] || i >= usable[r])
-          continue;
-        any = true;
-        const int src = 16 * r + i;
-        const int wi = __shfl_sync(0xffffffffu, w, src);
-        const int sti = tz_status(wi), vi = tz_value(wi);
-        if (sti == kTzExit) {
-          ans[r] = vi >= d[r];
-          open[r] = false;
-          continue;
-        }
-        uint32_t m = __shfl_sync(0xffffffffu, sm, src);
-        int R = d[r];
-        if (m) {
-          const unsigned long long Li = (unsigned long long)shfl_i64((int64_t)L, src);
-          while (m) {
-            const int k = __ffs(m);
-            m &= m - 1;
-            if (k > R)
-              break;
-            const int rr = k + thr_decode(int((Li >> (6 * (vi - k))) & 63));
-            R = rr > R ? rr : R;
-          }
-        }
-        if (R <= vi) {
-          ans[r] = true;
-          open[r] = false;
-        } else {
-          d[r] = R - vi;
+    // (words fetched ahead are as good as fresh ones unless they were empty)
+    int w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
+    while (tz_status(w) == kTzNone) {
+      w = ld_acquire(&words[u + 1]);
+      if (tz_status(w) != kTzNone)
+        break;
+      __nanosleep(pollNs);
+    }
+    const int st_ = tz_status(w), v = tz_value(w);
+    if (st_ == kTzExit)
+      return v + acc >= req;
+    if (st_ == kTzClassified) {
+      const unsigned long long L = lists[u + 1];
+      for (int i = v - 1; i >= 0; i--) {
+        const int pos = acc + (v - i);
+        if (pos > req)
+          return true;
+        const int code = int((L >> (6 * i)) & 63);
+        if (code >= 3) {
+          const int li = thr_decode(code);
+          if (pos + li > req)
+            req = pos + li;
         }
       }
-      if (!any)
-        break;
     }
-#pragma unroll
-    for (int r = 0; r < 2; r++)
-      if (open[r])
-        u[r] -= usable[r];
+    acc += v;
+    if (acc >= req)
+      return true;
+    u--;
   }
-  yes0 = ans[0];
-  yes1 = ans[1];
 }
 
 // processes block p (worklist rank t); called by all 32 lanes.
@@ -414,13 +316,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   const bool ext = cfg.ext != 0;
   const bool enc = cfg.isEncoder != 0;
   const bool rdoq = enc && !haar;
-  // the zero-run state of the blocks just before this one: asked for now, used
-  // once the block's own coefficients are classified (tz_runs_at_least)
-  TzPrefetch pf;
-  pf.w = 0;
-  pf.l = 0;
-  if (rdoq)
-    pf = tz_prefetch_words(a, t, lane);
 
   const int c0 = root ? 0 : P.first[p];
   uint32_t occ;
@@ -576,9 +471,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     : j == 6 ? 0x17u : j == 5 ? 0x57u : j == 3 ? 0x77u : 0x7fu;
   const int ncoef = __popc(existsMask);
   const int myPos = __popc(existsMask & before);
-
-  if (rdoq)
-    tz_prefetch_lists(a, t, lane, pf);
+  const int64_t coefPos = a.coefBase + c0 - (root ? 0 : p) + myPos;
+  // decoder: the coefficient comes from HBM and depends on nothing but the
+  // block's position: fetched now, not after the wait for the neighbours
+  int32_t qcIn = 0;
+  if (!enc && exists && act)
+    qcIn = my.coef[kk * my.coefStride + coefPos];
 
   //-- prediction (intraDcPred)
   int64_t pred = 0;
@@ -693,6 +591,19 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       pred = bfly_fwd(pred, bf[s], 1 << s, haar);
   }
 
+  // The zero-run words of the two blocks before this one, asked for as soon
+  // as the neighbours' values have arrived: on a chain of adjacent blocks the
+  // predecessor has just published its final word, and the round trip to L2
+  // overlaps the arithmetic up to the block's own classification instead of
+  // following it.
+  int wPre1 = 0, wPre2 = 0;
+  if (rdoq && act) {
+    if (t >= 1)
+      wPre1 = ld_acquire(&my.words[t]);
+    if (t >= 2)
+      wPre2 = ld_acquire(&my.words[t - 1]);
+  }
+
   if (enc && enablePred && exists)
     buf -= pred;
 
@@ -781,106 +692,60 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       st_release(&my.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
 
-    // Resolve the block's own decisions, all attributes together with all 32
-    // lanes (the look-back is a warp-wide operation): only coefficients with a
-    // finite threshold need the run length, everything between them extends
-    // it.  Per attribute: walk over its events (soft and always-resetting
-    // coefficients in scan order) up to the next one that has to ask; ask for
-    // all attributes at once; go on.
-    uint32_t sMq[2] = {0, 0}, hMq[2] = {0, 0}, ev[2] = {0, 0}, fl[2] = {0, 0};
-    unsigned long long cq[2] = {0, 0};
-    bool linked[2] = {true, true};  // the run still reaches back beyond the block
-    int z[2] = {0, 0};              // its length inside the block while linked
-    int tl[2] = {0, 0};             // run length since the last reset inside the block
-    int prev[2] = {0, 0};
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-      if (q < a.numSets) {
-        const int spk = 8 * a.set[q].base;
-        sMq[q] = __shfl_sync(0xffffffffu, softM, spk);
-        hMq[q] = __shfl_sync(0xffffffffu, hardM, spk);
-        cq[q] = (unsigned long long)shfl_i64((int64_t)codes, spk);
-        ev[q] = sMq[q] ? (sMq[q] | hMq[q]) : 0u;
-      }
-    for (;;) {
-      int need[2] = {0, 0};
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        while (ev[q]) {
-          const int m = __ffs(ev[q]) - 1;
-          if (linked[q])
-            z[q] += m - prev[q];
+    // resolve this block's own decisions (each lane for its attribute): only
+    // coefficients with a finite threshold need the run length, everything
+    // between them extends it
+    if (hasS) {
+      bool linked = true;  // the run still reaches back beyond the block
+      int z = 0;           // its length inside the block while linked
+      int tl = 0;          // run length since the last reset inside the block
+      int prev = 0;
+      uint32_t ev = softM | hardM;
+      while (ev) {
+        const int m = __ffs(ev) - 1;
+        ev &= ev - 1;
+        if (linked)
+          z += m - prev;
+        else
+          tl += m - prev;
+        prev = m + 1;
+        bool f = false;
+        if ((softM >> m) & 1) {
+          const int th = thr_decode(int((codes >> (6 * m)) & 63));
+          if (linked)
+            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2);
           else
-            tl[q] += m - prev[q];
-          prev[q] = m + 1;
-          bool f = false;
-          if ((sMq[q] >> m) & 1) {
-            const int th = thr_decode(int((cq[q] >> (6 * m)) & 63));
-            if (linked[q]) {
-              if (th - z[q] > 0) {
-                need[q] = th - z[q];  // has to ask; the event stays pending
-                break;
-              }
-              f = true;
-            } else {
-              f = tl[q] >= th;
-            }
-          }
-          if (linked[q]) {
-            if (f)
-              z[q]++;
-            else {
-              linked[q] = false;
-              tl[q] = 0;
-            }
-          } else {
-            tl[q] = f ? tl[q] + 1 : 0;
-          }
+            f = tl >= th;
+        }
+        if (linked) {
           if (f)
-            fl[q] |= 1u << m;
-          ev[q] &= ev[q] - 1;
-        }
-      }
-      if (need[0] <= 0 && need[1] <= 0)
-        break;
-      bool yes[2];
-      tz_runs_at_least(a, t, need[0], need[1], pf, lane, yes[0], yes[1]);
-#pragma unroll
-      for (int q = 0; q < 2; q++)
-        if (need[q] > 0) {  // the pending event: a soft coefficient of a linked run
-          const int m = __ffs(ev[q]) - 1;
-          if (yes[q]) {
-            z[q]++;
-            fl[q] |= 1u << m;
-          } else {
-            linked[q] = false;
-            tl[q] = 0;
+            z++;
+          else {
+            linked = false;
+            tl = 0;
           }
-          ev[q] &= ev[q] - 1;
+        } else {
+          tl = f ? tl + 1 : 0;
         }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-      if (q < a.numSets && sMq[q]) {
-        tl[q] += ncoef - prev[q];
-        if (!hMq[q] && lane == 8 * a.set[q].base)
-          st_release(&a.set[q].words[t + 1],
-                     linked[q] ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl[q]));
+        if (m == myPos)
+          flagMine = f;
       }
-    if (hasS && ((softM >> myPos) & 1))
-      flagMine = ((si ? fl[1] : fl[0]) >> myPos) & 1;
+      tl += ncoef - prev;
+      if (!hasH && speaker)
+        st_release(&my.words[t + 1],
+                   linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
+    }
   }
 
   //-- quantise / dequantise (RAHT.cpp:1672-1723)
   if (exists && act) {
     const Quantizer& qk = qz[kk < 1 ? kk : 1];
-    const int64_t pos = a.coefBase + c0 - (root ? 0 : p) + myPos;
     int64_t qc;
     if (enc) {
       qc = flagMine ? 0 : qcMine;
-      my.coef[kk * my.coefStride + pos] = int32_t(qc);
+      my.coef[kk * my.coefStride + coefPos] = int32_t(qc);
     } else {
-      qc = my.coef[kk * my.coefStride + pos];
+      qc = qcIn;
     }
     pred += fx_from_int(div_exp2_round_half_up(qk.scale(qc), kAttrShift));
   }
