@@ -63,7 +63,7 @@ METRIC = "attribute-transform Mpoints/s (RAHT forward: Morton sort + transform, 
 ALG_BYTES_PER_POINT = (16 + 12 * 3) + (16 + 12 * 1)  # 52 (RGB) + 28 (reflectance)
 
 
-FRAMES_PER_STEP = 16
+FRAMES_PER_STEP = 32  # one fused call (colour + reflectance) per frame: one lane each
 
 
 def workload_config(frames=FRAMES_PER_STEP):

@@ -171,6 +171,10 @@ struct WaveDescent<DeviceExec> {
       return e && !strcmp(e, "morton");
     }();
     const bool wave = cfg.predictionEnabled && cfg.subnode && !rdoq && !mortonOrder;
+    static const int handOver = [] {  // A/B: 0 = every hand-over through L2
+      const char* e = getenv("PCCB200_HANDOVER");
+      return e ? atoi(e) : 1;
+    }();
 
     //-- row space: one segment per descent step below the root
     LevelArgs la = {};
@@ -225,6 +229,7 @@ struct WaveDescent<DeviceExec> {
       a.ab11a = abA;
       a.ab11b = abB;
       a.pollNs = pollNs;
+      a.handOver = handOver;
     }
     for (int d = 1; d <= top; d++) {
       const int si = top - d;
