@@ -223,6 +223,8 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 // is on the critical path of the whole stage, saves the L2 round trips.
 // A slot belongs to ticket `rank` (slot = rank & 15); `p` is the block index
 // once rec[] holds its reconstruction (lane = component row * 8 + child slot).
+// Only the current owner writes a slot: a block waits at its start until the
+// previous owner of its slot (a lower ticket of the same CTA) has finished.
 // Readers validate after reading (the slot may have moved on to a later
 // ticket); anything not found here is read from global memory as before.
 constexpr int kHandSlots = 16;
@@ -230,6 +232,7 @@ constexpr int kBatch = 8;  // tickets a CTA takes at a time (= warps per CTA)
 struct HandOver {
   int rank;
   int p;
+  int done;  // the owner has finished writing (the slot may be given to a later ticket)
   int word[kMaxSets];
   unsigned long long list[kMaxSets];
   long long rec[32];
@@ -363,6 +366,9 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
   int prevP1 = -1, prevP2 = -1;
   if (hs) {
     if (lane == 0) {
+      while (me->done == 0)  // (a lower ticket: finishes without anything of this block)
+        __nanosleep(20);
+      me->done = 0;
       me->word[0] = 0;
       me->word[1] = 0;
       me->p = -1;
@@ -884,6 +890,8 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
     if (lane == 0) {
       __threadfence_block();
       me->p = p;
+      __threadfence_block();
+      me->done = 1;
     }
   }
   if (present && act) {
@@ -952,8 +960,9 @@ __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
   __shared__ HandOver sHand[kHandSlots];
-  __shared__ unsigned long long sBatch[4];  // (batch number + 1) << 40 | first ticket
-  __shared__ int sClaim;
+  // the CTA's current batch of tickets: first ticket << 8 | tickets handed out
+  // (>= kBatch: used up; the warp that draws exactly kBatch fetches the next)
+  __shared__ unsigned long long sState;
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
   // coding order with a worklist: tickets by the batch, hand-over through shared memory
@@ -962,11 +971,10 @@ k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
     if (threadIdx.x < kHandSlots) {
       sHand[threadIdx.x].rank = -1;
       sHand[threadIdx.x].p = -1;
+      sHand[threadIdx.x].done = 1;
     }
-    if (threadIdx.x < 4)
-      sBatch[threadIdx.x] = 0;
     if (threadIdx.x == 0)
-      sClaim = 0;
+      sState = kBatch;
     __syncthreads();
   }
   for (;;) {
@@ -974,21 +982,24 @@ k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
     int base = 0;
     if (batched) {
       if (lane == 0) {
-        const int idx = atomicAdd(&sClaim, 1);
-        const unsigned long long b = (unsigned long long)(idx / kBatch);
-        const int w = idx % kBatch;
-        volatile unsigned long long* slot = &sBatch[b & 3];
-        unsigned long long v;
-        if (w == 0) {
-          v = atomicAdd(ticket, (unsigned long long)kBatch);
-          *slot = ((b + 1) << 40) | v;
-        } else {
-          while (((v = *slot) >> 40) != b + 1)
+        for (;;) {
+          const unsigned long long st = atomicAdd(&sState, 1ull);
+          const int w = int(st & 0xff);
+          if (w < kBatch) {
+            base = int(st >> 8);
+            tk = (st >> 8) + w;
+            break;
+          }
+          if (w == kBatch) {  // first to find the batch used up: fetch the next one
+            const unsigned long long v = atomicAdd(ticket, (unsigned long long)kBatch);
+            atomicExch(&sState, (v << 8) | 1ull);  // (ticket v + 0 is this warp's)
+            base = int(v);
+            tk = v;
+            break;
+          }
+          while ((*(volatile unsigned long long*)&sState & 0xff) >= kBatch)
             __nanosleep(20);
-          v &= (1ull << 40) - 1;
         }
-        tk = v + w;
-        base = int(v);
       }
       tk = __shfl_sync(0xffffffffu, tk, 0);
       base = __shfl_sync(0xffffffffu, base, 0);
