@@ -256,6 +256,49 @@ int pccb200_attr_raht_decode_multi_dev(const pccb200_raht_params* params, int32_
                                        const int32_t* num_attrs, const int32_t* bitdepths,
                                        int32_t n, const int32_t* const* d_coeffs_in);
 
+/* Many coding units in one call ----------------------------------------------
+ *
+ * The slices of a frame (tmc3/TMC3.cpp:781-810 cuts a frame into slices of at
+ * most sliceMaxPoints points; tmc3/encoder.cpp:545-568 codes them one after
+ * another) and the frames of a sequence are independent point sets.  A unit
+ * whose coefficients are dense in small values is bound by the latency of its
+ * own chain of blocks (the zero-run state of the encoder's RDOQ runs through
+ * every coefficient in coding order, tmc3/RAHT.cpp:1154,1617-1670) and keeps
+ * only a few warps busy: device throughput follows the number of units in
+ * flight.  These entry points take num_units units with the same attributes
+ * (num_sets, num_attrs[s], bitdepths[s], qpsets[s] as above) and code them in
+ * gangs: the top-down passes of all units of a gang share their kernel
+ * launches, so the units in flight are not limited by the number of streams.
+ * Results are bit-identical to one pccb200_attr_raht_*_multi call per unit.
+ *
+ *   xyz[u] (n[u] x 3), attrs[u * num_sets + s] (n[u] x num_attrs[s], in/out),
+ *   coeffs[u * num_sets + s] (num_attrs[s] planes of n[u]) describe unit u.
+ * The pointer arrays are host arrays; in the *_dev variants their elements are
+ * device pointers (stream-ordering note above).  Workspace: about 0.6 KB per
+ * point and unit in flight. */
+int pccb200_attr_raht_encode_multi_batch(const pccb200_raht_params* params, int32_t num_sets,
+                                         const pccb200_qpset* const* qpsets, int32_t num_units,
+                                         const int32_t* const* xyz, int32_t* const* attrs_inout,
+                                         const int32_t* num_attrs, const int32_t* bitdepths,
+                                         const int32_t* n, int32_t* const* coeffs_out);
+int pccb200_attr_raht_decode_multi_batch(const pccb200_raht_params* params, int32_t num_sets,
+                                         const pccb200_qpset* const* qpsets, int32_t num_units,
+                                         const int32_t* const* xyz, int32_t* const* attrs_out,
+                                         const int32_t* num_attrs, const int32_t* bitdepths,
+                                         const int32_t* n, const int32_t* const* coeffs_in);
+int pccb200_attr_raht_encode_multi_batch_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                             const pccb200_qpset* const* qpsets,
+                                             int32_t num_units, const int32_t* const* d_xyz,
+                                             int32_t* const* d_attrs_inout,
+                                             const int32_t* num_attrs, const int32_t* bitdepths,
+                                             const int32_t* n, int32_t* const* d_coeffs_out);
+int pccb200_attr_raht_decode_multi_batch_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                             const pccb200_qpset* const* qpsets,
+                                             int32_t num_units, const int32_t* const* d_xyz,
+                                             int32_t* const* d_attrs_out,
+                                             const int32_t* num_attrs, const int32_t* bitdepths,
+                                             const int32_t* n, const int32_t* const* d_coeffs_in);
+
 /* Per-phase device timing (CUDA events around every kernel launch on
  * the call's stream).  Phases: 0 Morton keys + radix sort, 1 tree build
  * (histogram, compaction, leaf / merge kernels), 2 block transform (the

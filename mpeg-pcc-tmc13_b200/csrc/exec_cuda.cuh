@@ -505,10 +505,9 @@ struct DeviceExec {
     // CTAs retire between stages.
     const int inFlight = activeCalls ? activeCalls->load() : 1;
     int64_t cap = int64_t(numSMs) * perSM;
-    static const int capShare = [] {  // percent of the machine all calls in flight may hold
-      const char* e = getenv("PCCB200_BLOCK_SHARE");
-      return e ? atoi(e) : 100;
-    }();
+    // percent of the machine all calls in flight may hold (A/B knob, read per call)
+    const char* es = getenv("PCCB200_BLOCK_SHARE");
+    const int capShare = es ? atoi(es) : 100;
     if (inFlight > 1)
       cap = cap * capShare / (100 * inFlight);
     static const int envCap = [] {

@@ -360,42 +360,83 @@ attr_raht_slice(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
 
 // one slice, several attributes on the same positions in one pass: one sort,
 // one tree, one dependency chain.  Pointers as in attr_raht_slice, one per set.
+// In two halves, so that the descents of several slices can be issued together
+// (a gang, attr_raht_batch_common): _begin sorts, gathers, builds the tree and
+// either runs the descent or leaves it prepared in ms.defer; _end runs the
+// duplicate tail (if deferred) and scatters the reconstruction back.
 // PCCB200_ERR_UNSUPPORTED: this parameter combination has no fused path.
+struct MultiSlice {
+  int32_t* dOrder = nullptr;
+  int32_t* dAttrs = nullptr;
+  int AT = 0;
+  RahtDeferred<DeviceExec> defer;
+};
+
 int
-attr_raht_slice_multi(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
-                      int numSets, const pccb200_qpset* const* qpsets, const int32_t* dXyz,
-                      const int32_t* const* dAttrsIn, int32_t* const* dAttrsOut, const int* A,
-                      const int* bitdepth, int n, int32_t* const* dCoef, const int64_t* coefStride)
+attr_raht_slice_multi_begin(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
+                            int numSets, const pccb200_qpset* const* qpsets, const int32_t* dXyz,
+                            const int32_t* const* dAttrsIn, const int* A, int n,
+                            int32_t* const* dCoef, const int64_t* coefStride, MultiSlice& ms,
+                            bool deferDescent)
 {
   int AT = 0;
   for (int s = 0; s < numSets; s++)
     AT += A[s];
   int64_t* dKeys = ex.alloc<int64_t>(size_t(n));
-  int32_t* dOrder = ex.alloc<int32_t>(size_t(n));
-  int32_t* dAttrs = ex.alloc<int32_t>(size_t(n) * AT);
-  device_morton_sort(ex, dXyz, n, dKeys, dOrder);
+  ms.dOrder = ex.alloc<int32_t>(size_t(n));
+  ms.dAttrs = ex.alloc<int32_t>(size_t(n) * AT);
+  ms.AT = AT;
+  device_morton_sort(ex, dXyz, n, dKeys, ms.dOrder);
   const unsigned g = grid_for(n, ex.numSMs);
   ex.phase(kPhaseGather);
   RahtSetIO io[2];
   for (int s = 0, base = 0; s < numSets; base += A[s], s++) {
     if (forward) {
       DeviceExec::Scope sc(ex);
-      k_gather_rows_strided<<<g, 256, 0, ex.stream>>>(dAttrsIn[s], dOrder, n, A[s], dAttrs, AT, base);
+      k_gather_rows_strided<<<g, 256, 0, ex.stream>>>(dAttrsIn[s], ms.dOrder, n, A[s], ms.dAttrs, AT, base);
       g_launchCount++;
     }
     io[s] = RahtSetIO{qpsets[s], A[s], dCoef[s], coefStride[s]};
   }
-  int rc = raht_run_sets(ex, *params, numSets, io, forward, dKeys, dAttrs, nullptr, n);
+  int rc = raht_run_sets(ex, *params, numSets, io, forward, dKeys, ms.dAttrs, nullptr, n,
+                         deferDescent ? &ms.defer : nullptr);
   if (rc != PCCB200_OK)
     return rc == PCCB200_ERR_UNSUPPORTED ? rc : fail(rc, "invalid parameters");
+  return PCCB200_OK;
+}
+
+void
+attr_raht_slice_multi_end(DeviceExec& ex, int numSets, const int* A, const int* bitdepth, int n,
+                          int32_t* const* dAttrsOut, MultiSlice& ms)
+{
+  if (ms.defer.pending) {
+    ex.phase(kPhaseTail);
+    ex.foreach(ms.defer.nLeaves, ms.defer.tail);
+    ms.defer.pending = false;
+  }
+  const unsigned g = grid_for(n, ex.numSMs);
   ex.phase(kPhaseGather);
   for (int s = 0, base = 0; s < numSets; base += A[s], s++) {
     DeviceExec::Scope sc(ex);
-    k_scatter_rows_clip_strided<<<g, 256, 0, ex.stream>>>(dAttrs, AT, base, dOrder, n, A[s],
+    k_scatter_rows_clip_strided<<<g, 256, 0, ex.stream>>>(ms.dAttrs, ms.AT, base, ms.dOrder, n, A[s],
                                                           (1 << bitdepth[s]) - 1, dAttrsOut[s]);
     g_launchCount++;
   }
   PCC_CUDA_CHECK(cudaGetLastError());
+}
+
+int
+attr_raht_slice_multi(DeviceExec& ex, bool forward, const pccb200_raht_params* params,
+                      int numSets, const pccb200_qpset* const* qpsets, const int32_t* dXyz,
+                      const int32_t* const* dAttrsIn, int32_t* const* dAttrsOut, const int* A,
+                      const int* bitdepth, int n, int32_t* const* dCoef, const int64_t* coefStride)
+{
+  MultiSlice ms;
+  int rc = attr_raht_slice_multi_begin(ex, forward, params, numSets, qpsets, dXyz, dAttrsIn, A, n,
+                                       dCoef, coefStride, ms, false);
+  if (rc != PCCB200_OK)
+    return rc;
+  attr_raht_slice_multi_end(ex, numSets, A, bitdepth, n, dAttrsOut, ms);
   return PCCB200_OK;
 }
 
@@ -554,6 +595,107 @@ attr_raht_multi_common(bool forward, bool device, const pccb200_raht_params* par
       return rc;
   }
   return PCCB200_OK;
+}
+
+// Many coding units (the slices of a frame, or whole frames: independent
+// point sets, each with the same attributes) in one call.  The units are dealt
+// to the lanes in gangs: a lane sorts / builds the tree of each unit of its
+// gang in turn and then issues the top-down passes of all of them together,
+// one launch per descent step (WaveDescent::run_gang).  A textured unit keeps
+// only a few warps busy (its blocks form one chain): the number of chains in
+// flight is what the device's throughput follows, and with gangs it is no
+// longer limited by the number of hardware queues.
+constexpr int kMaxGang = 32;
+
+int
+attr_raht_batch_common(bool forward, bool device, const pccb200_raht_params* params, int numSets,
+                       const pccb200_qpset* const* qpsets, int numUnits,
+                       const int32_t* const* xyz, int32_t* const* attrs, const int32_t* A,
+                       const int32_t* bitdepth, const int32_t* n, int32_t* const* coeffs)
+{
+  if (!xyz || !attrs || !coeffs || !n || numUnits <= 0)
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  for (int u = 0; u < numUnits; u++) {
+    if (!xyz[u])
+      return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+    int rc = check_multi(params, numSets, qpsets, xyz[u],
+                         reinterpret_cast<const void* const*>(attrs + size_t(u) * numSets), A,
+                         bitdepth, reinterpret_cast<const void* const*>(coeffs + size_t(u) * numSets),
+                         n[u]);
+    if (rc != PCCB200_OK)
+      return rc;
+  }
+  // the fused pass exists for these parameters?  (same test as raht_run_sets)
+  bool fused = true;
+  if (numSets > 1)
+    for (int u = 0; u < numUnits && fused; u++) {
+      fused = n[u] >= 2;
+      for (int s = 0; s < numSets && fused; s++)
+        fused = WaveDescent<DeviceExec>::enabled(make_config(*params, *qpsets[s], forward, A[s], false));
+    }
+  if (!fused)  // unit by unit, attribute by attribute (results do not depend on the route)
+    return parallel_for(numUnits, kMaxSliceThreads, [&](int u) -> int {
+      return attr_raht_multi_common(forward, device, params, numSets, qpsets, xyz[u],
+                                    attrs + size_t(u) * numSets, A, bitdepth, n[u],
+                                    coeffs + size_t(u) * numSets);
+    });
+  // units per gang: by default the units are spread over all lanes first
+  // (PCCB200_GANG: A/B knob, read per call)
+  const char* eg = getenv("PCCB200_GANG");
+  const int envGang = eg ? atoi(eg) : 0;
+  int gang = envGang > 0 ? envGang : (numUnits + kMaxLanes - 1) / kMaxLanes;
+  gang = gang > kMaxGang ? kMaxGang : gang;
+  const int numGangs = (numUnits + gang - 1) / gang;
+  return parallel_for(numGangs, kMaxLanes, [&](int g) -> int {
+    const int u0 = g * gang;
+    const int u1 = u0 + gang < numUnits ? u0 + gang : numUnits;
+    const int m = u1 - u0;
+    return with_device([&](DeviceExec& ex) -> int {
+      std::vector<MultiSlice> ms(m);
+      std::vector<int32_t*> dOut(size_t(m) * 2), dCoef(size_t(m) * 2);
+      for (int i = 0; i < m; i++) {
+        const int u = u0 + i;
+        const int nu = n[u];
+        const int32_t* dXyz = device ? xyz[u] : to_device(ex, xyz[u], size_t(nu) * 3);
+        int32_t* dIn[2] = {nullptr, nullptr};
+        int64_t stride[2] = {nu, nu};
+        for (int s = 0; s < numSets; s++) {
+          int32_t* a = attrs[size_t(u) * numSets + s];
+          int32_t* c = coeffs[size_t(u) * numSets + s];
+          if (device) {
+            dIn[s] = dOut[2 * i + s] = a;
+            dCoef[2 * i + s] = c;
+          } else {
+            dIn[s] = forward ? to_device(ex, a, size_t(nu) * A[s]) : nullptr;
+            dOut[2 * i + s] = ex.alloc<int32_t>(size_t(nu) * A[s]);
+            dCoef[2 * i + s] = forward ? ex.alloc<int32_t>(size_t(nu) * A[s])
+                                       : to_device(ex, c, size_t(nu) * A[s]);
+          }
+        }
+        int rc2 = attr_raht_slice_multi_begin(ex, forward, params, numSets, qpsets, dXyz, dIn, A, nu,
+                                              &dCoef[2 * i], stride, ms[i], true);
+        if (rc2 != PCCB200_OK)
+          return rc2;
+      }
+      std::vector<WaveDescent<DeviceExec>::Job*> jobs;
+      for (int i = 0; i < m; i++)
+        if (ms[i].defer.pending)
+          jobs.push_back(&ms[i].defer.job);
+      if (!jobs.empty())
+        WaveDescent<DeviceExec>::run_gang(ex, jobs.data(), int(jobs.size()));
+      for (int i = 0; i < m; i++) {
+        const int u = u0 + i;
+        attr_raht_slice_multi_end(ex, numSets, A, bitdepth, n[u], &dOut[2 * i], ms[i]);
+        if (!device)
+          for (int s = 0; s < numSets; s++) {
+            to_host(ex, attrs[size_t(u) * numSets + s], dOut[2 * i + s], size_t(n[u]) * A[s]);
+            if (forward)
+              to_host(ex, coeffs[size_t(u) * numSets + s], dCoef[2 * i + s], size_t(n[u]) * A[s]);
+          }
+      }
+      return PCCB200_OK;
+    });
+  });
 }
 
 }  // namespace
@@ -766,6 +908,52 @@ pccb200_attr_raht_decode_multi_dev(const pccb200_raht_params* params, int32_t nu
 {
   return attr_raht_multi_common(false, true, params, num_sets, qpsets, d_xyz, d_attrs_out,
                                 num_attrs, bitdepths, n,
+                                const_cast<int32_t* const*>(d_coeffs_in));
+}
+
+int
+pccb200_attr_raht_encode_multi_batch(const pccb200_raht_params* params, int32_t num_sets,
+                                     const pccb200_qpset* const* qpsets, int32_t num_units,
+                                     const int32_t* const* xyz, int32_t* const* attrs_inout,
+                                     const int32_t* num_attrs, const int32_t* bitdepths,
+                                     const int32_t* n, int32_t* const* coeffs_out)
+{
+  return attr_raht_batch_common(true, false, params, num_sets, qpsets, num_units, xyz,
+                                attrs_inout, num_attrs, bitdepths, n, coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode_multi_batch(const pccb200_raht_params* params, int32_t num_sets,
+                                     const pccb200_qpset* const* qpsets, int32_t num_units,
+                                     const int32_t* const* xyz, int32_t* const* attrs_out,
+                                     const int32_t* num_attrs, const int32_t* bitdepths,
+                                     const int32_t* n, const int32_t* const* coeffs_in)
+{
+  return attr_raht_batch_common(false, false, params, num_sets, qpsets, num_units, xyz, attrs_out,
+                                num_attrs, bitdepths, n, const_cast<int32_t* const*>(coeffs_in));
+}
+
+int
+pccb200_attr_raht_encode_multi_batch_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                         const pccb200_qpset* const* qpsets, int32_t num_units,
+                                         const int32_t* const* d_xyz,
+                                         int32_t* const* d_attrs_inout, const int32_t* num_attrs,
+                                         const int32_t* bitdepths, const int32_t* n,
+                                         int32_t* const* d_coeffs_out)
+{
+  return attr_raht_batch_common(true, true, params, num_sets, qpsets, num_units, d_xyz,
+                                d_attrs_inout, num_attrs, bitdepths, n, d_coeffs_out);
+}
+
+int
+pccb200_attr_raht_decode_multi_batch_dev(const pccb200_raht_params* params, int32_t num_sets,
+                                         const pccb200_qpset* const* qpsets, int32_t num_units,
+                                         const int32_t* const* d_xyz, int32_t* const* d_attrs_out,
+                                         const int32_t* num_attrs, const int32_t* bitdepths,
+                                         const int32_t* n, const int32_t* const* d_coeffs_in)
+{
+  return attr_raht_batch_common(false, true, params, num_sets, qpsets, num_units, d_xyz,
+                                d_attrs_out, num_attrs, bitdepths, n,
                                 const_cast<int32_t* const*>(d_coeffs_in));
 }
 

@@ -61,7 +61,6 @@ struct WarpBlockArgs {
   // order[i] (worklist rank + orderBase), rows sorted by dependency level
   const int32_t* order;
   int orderBase;
-  int handOver;  // coding order: batches of tickets per CTA, hand-over through shared memory
 };
 
 // Zero-run bookkeeping of one stage, indexed by worklist rank t:
@@ -215,29 +214,6 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
   return kCodeHard;
 }
 
-// Hand-over through shared memory.  In coding order a CTA takes its tickets
-// eight at a time, one per warp, so that the blocks of a chain of adjacent
-// blocks mostly sit in the same CTA: what a block hands to the next one (the
-// reconstruction of its children, its zero-run words) then goes through a
-// ring of shared-memory slots as well as through L2, and the consumer, which
-// is on the critical path of the whole stage, saves the L2 round trips.
-// A slot belongs to ticket `rank` (slot = rank & 15); `p` is the block index
-// once rec[] holds its reconstruction (lane = component row * 8 + child slot).
-// Only the current owner writes a slot: a block waits at its start until the
-// previous owner of its slot (a lower ticket of the same CTA) has finished.
-// Readers validate after reading (the slot may have moved on to a later
-// ticket); anything not found here is read from global memory as before.
-constexpr int kHandSlots = 16;
-constexpr int kBatch = 8;  // tickets a CTA takes at a time (= warps per CTA)
-struct HandOver {
-  int rank;
-  int p;
-  int done;  // the owner has finished writing (the slot may be given to a later ticket)
-  int word[kMaxSets];
-  unsigned long long list[kMaxSets];
-  long long rec[32];
-};
-
 // Is the run of non-resetting coefficients that ends just before block t of
 // stage a.stageIdx at least `need` long?  Walks back over the published
 // classification of earlier blocks (this stage, then earlier stages); waits
@@ -253,12 +229,10 @@ struct HandOver {
 // 392 ms against 304 ms on the textured frame): what bounds a stage there is
 // not the memory latency of the walk but the instruction issue the waiting
 // warps take from the one warp that can make progress, and a heavier loop
-// around the poll makes every waiting warp more expensive.  (Fetching the two
-// predecessors' words as soon as the neighbours' values are in, so that the
-// round trip overlaps the block's own classification: no gain either, 365 ms.)
+// around the poll makes every waiting warp more expensive.
 __device__ __forceinline__ bool
 tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, int need,
-                volatile HandOver* hs, const int batchBase, const int si)
+                const int wPre1, const int wPre2)
 {
   if (need <= 0)
     return true;
@@ -278,35 +252,19 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
       u = *rg.count - 1;
       continue;
     }
-    int w = 0;
-    unsigned long long L = 0;
-    bool haveList = false;
-    if (hs && s == stageIdx && u >= batchBase) {
-      // a block of this CTA's batch: its words go through shared memory
-      volatile HandOver* h = &hs[u & (kHandSlots - 1)];
-      while (h->rank == u) {
-        const int ws = h->word[si];
-        if (tz_status(ws) != kTzNone) {
-          const unsigned long long ls = h->list[si];
-          if (h->rank == u) {  // still that block's slot: the pair is its own
-            w = ws;
-            L = ls;
-            haveList = true;
-          }
-          break;
-        }
-        __nanosleep(20);
-      }
+    // (words fetched ahead are as good as fresh ones unless they were empty)
+    int w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
+    while (tz_status(w) == kTzNone) {
+      w = ld_acquire(&words[u + 1]);
+      if (tz_status(w) != kTzNone)
+        break;
+      __nanosleep(pollNs);
     }
-    if (tz_status(w) == kTzNone)
-      while (tz_status(w = ld_acquire(&words[u + 1])) == kTzNone)
-        __nanosleep(pollNs);
     const int st_ = tz_status(w), v = tz_value(w);
     if (st_ == kTzExit)
       return v + acc >= req;
     if (st_ == kTzClassified) {
-      if (!haveList)
-        L = lists[u + 1];
+      const unsigned long long L = lists[u + 1];
       for (int i = v - 1; i >= 0; i--) {
         const int pos = acc + (v - i);
         if (pos > req)
@@ -335,8 +293,7 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
 // quantisers, the inherited DC), do all the arithmetic that needs only those,
 // and only then look at the values still being produced.
 __device__ __forceinline__ void
-warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
-           volatile HandOver* hs, const int batchBase)
+warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
 {
   const RahtConfig& cfg = a.cfg;
   const Stage& S = a.S;
@@ -359,28 +316,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
   const bool ext = cfg.ext != 0;
   const bool enc = cfg.isEncoder != 0;
   const bool rdoq = enc && !haar;
-
-  // this block's hand-over slot, and the blocks of the two tickets before it
-  // (if they belong to the same batch): the likely end of the chain it is on
-  volatile HandOver* me = hs ? &hs[t & (kHandSlots - 1)] : nullptr;
-  int prevP1 = -1, prevP2 = -1;
-  if (hs) {
-    if (lane == 0) {
-      while (me->done == 0)  // (a lower ticket: finishes without anything of this block)
-        __nanosleep(20);
-      me->done = 0;
-      me->word[0] = 0;
-      me->word[1] = 0;
-      me->p = -1;
-      __threadfence_block();
-      me->rank = t;
-    }
-    __syncwarp();
-    if (t - 1 >= batchBase)
-      prevP1 = a.worklist[t - 1];
-    if (t - 2 >= batchBase)
-      prevP2 = a.worklist[t - 2];
-  }
 
   const int c0 = root ? 0 : P.first[p];
   uint32_t occ;
@@ -596,18 +531,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
     // loads of up to four neighbours go out together, then whatever has not
     // been produced yet is polled
     uint32_t cm = childNb;
-    uint32_t localNb = 0;  // neighbours whose block is one of the two tickets before this one
-    if (hs) {
-      uint32_t c2 = cm;
-      while (c2) {
-        const int i = __ffs(c2) - 1;
-        c2 &= c2 - 1;
-        const int qi = __shfl_sync(0xffffffffu, nq, i);
-        if (qi == prevP1 || qi == prevP2)
-          localNb |= 1u << i;
-      }
-      cm &= ~localNb;
-    }
     while (cm) {
       int64_t v[4];
       const int64_t* ad[4];
@@ -653,49 +576,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
       for (int u = 0; u < 4; u++)
         pred += v[u] * (wc[u] * fracMul);
     }
-    // the neighbours of this CTA's batch last (they are the ones still being
-    // produced): through shared memory
-    while (localNb) {
-      const int i = __ffs(localNb) - 1;
-      localNb &= localNb - 1;
-      const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
-      const int cfirst = __shfl_sync(0xffffffffu, nfirst, i);
-      const int qi = __shfl_sync(0xffffffffu, nq, i);
-      const int ii = i - 7;
-      const int sh = occu_shift(ii);
-      const int shift = ii < 9 ? sh : -sh;
-      const uint32_t cmask =
-        (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
-      const bool need = act && ((cmask >> j) & 1) && ((validMask >> i) & 1);
-      const int r = qi == prevP1 ? t - 1 : t - 2;
-      volatile HandOver* h = &hs[r & (kHandSlots - 1)];
-      int64_t val = 0;
-      bool got = false;
-      for (;;) {
-        if (h->p == qi) {
-          val = need ? h->rec[(j + shift) + 8 * k] : 0;
-          if (h->p == qi) {  // still that block: the values are its own
-            got = true;
-            break;
-          }
-        }
-        if (h->rank > r)
-          break;  // the slot has moved on: the values are in global memory by now
-        __nanosleep(20);
-      }
-      if (!got) {
-        const int c = cfirst + __popc(no & ((1u << (j + shift)) - 1));
-        const int64_t* ad1 = need ? &S.rec[size_t(c) * A + k] : nullptr;
-        val = ad1 ? ld_rec(ad1) : 0;
-        while (__any_sync(0xffffffffu, ad1 && val == kRecNotReady)) {
-          __nanosleep(a.pollNs);
-          if (ad1 && val == kRecNotReady)
-            val = ld_rec(ad1);
-        }
-      }
-      if (need)
-        pred += val * (cfg.predWeightChild[ii] * fracMul);
-    }
     if (present && act) {
       int64_t v = fx_mul(pred, div);
       if (haar)
@@ -709,6 +589,19 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
 #pragma unroll
     for (int s = 0; s < 3; s++)
       pred = bfly_fwd(pred, bf[s], 1 << s, haar);
+  }
+
+  // The zero-run words of the two blocks before this one, asked for as soon
+  // as the neighbours' values have arrived: on a chain of adjacent blocks the
+  // predecessor has just published its final word, and the round trip to L2
+  // overlaps the arithmetic up to the block's own classification instead of
+  // following it.
+  int wPre1 = 0, wPre2 = 0;
+  if (rdoq && act) {
+    if (t >= 1)
+      wPre1 = ld_acquire(&my.words[t]);
+    if (t >= 2)
+      wPre2 = ld_acquire(&my.words[t - 1]);
   }
 
   if (enc && enablePred && exists)
@@ -789,23 +682,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         prev = m + 1;
       }
       e += ncoef - prev;
-      if (speaker) {
-        if (me)
-          me->word[si] = tz_pack(kTzExit, e);
+      if (speaker)
         st_release(&my.words[t + 1], tz_pack(kTzExit, e));
-      }
     } else if (!hasS) {
-      if (speaker) {
-        if (me)
-          me->word[si] = tz_pack(kTzTransparent, ncoef);
+      if (speaker)
         st_release(&my.words[t + 1], tz_pack(kTzTransparent, ncoef));
-      }
     } else if (speaker) {
-      if (me) {
-        me->list[si] = codes;
-        __threadfence_block();
-        me->word[si] = tz_pack(kTzClassified, ncoef);
-      }
       my.lists[t + 1] = codes;
       st_release(&my.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
@@ -831,7 +713,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         if ((softM >> m) & 1) {
           const int th = thr_decode(int((codes >> (6 * m)) & 63));
           if (linked)
-            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, hs, batchBase, si);
+            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2);
           else
             f = tl >= th;
         }
@@ -849,12 +731,9 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
           flagMine = f;
       }
       tl += ncoef - prev;
-      if (!hasH && speaker) {
-        const int fw = linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl);
-        if (me)
-          me->word[si] = fw;
-        st_release(&my.words[t + 1], fw);
-      }
+      if (!hasH && speaker)
+        st_release(&my.words[t + 1],
+                   linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
     }
   }
 
@@ -877,26 +756,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
 #pragma unroll
   for (int s = 2; s >= 0; s--)
     pred = bfly_inv(pred, bf[s], 1 << s, haar);
-  int64_t recOut = 0;
   if (present && act) {
     int64_t v = pred;
+    S.recUs[size_t(cidx) * A + k] = ext ? v : fx_round(v * 4);
     if (rsMul)
       v = fx_mul(v >> rsShift, rsMul);
-    recOut = ext ? v : fx_round(v);
-  }
-  if (me) {  // first where the next block of the chain looks first
-    me->rec[lane] = recOut;
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      me->p = p;
-      __threadfence_block();
-      me->done = 1;
-    }
-  }
-  if (present && act) {
-    st_rec(&S.rec[size_t(cidx) * A + k], recOut);
-    S.recUs[size_t(cidx) * A + k] = ext ? pred : fx_round(pred * 4);
+    st_rec(&S.rec[size_t(cidx) * A + k], ext ? v : fx_round(v));
   }
 }
 
@@ -959,60 +824,59 @@ k_block_geom(const WarpBlockArgs a)
 __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
-  __shared__ HandOver sHand[kHandSlots];
-  // the CTA's current batch of tickets: first ticket << 8 | tickets handed out
-  // (>= kBatch: used up; the warp that draws exactly kBatch fetches the next)
-  __shared__ unsigned long long sState;
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
-  // coding order with a worklist: tickets by the batch, hand-over through shared memory
-  const bool batched = a.order == nullptr && a.worklist != nullptr && a.handOver;
-  if (batched) {
-    if (threadIdx.x < kHandSlots) {
-      sHand[threadIdx.x].rank = -1;
-      sHand[threadIdx.x].p = -1;
-      sHand[threadIdx.x].done = 1;
-    }
-    if (threadIdx.x == 0)
-      sState = kBatch;
-    __syncthreads();
-  }
   for (;;) {
-    unsigned long long tk = 0;
-    int base = 0;
-    if (batched) {
-      if (lane == 0) {
-        for (;;) {
-          const unsigned long long st = atomicAdd(&sState, 1ull);
-          const int w = int(st & 0xff);
-          if (w < kBatch) {
-            base = int(st >> 8);
-            tk = (st >> 8) + w;
-            break;
-          }
-          if (w == kBatch) {  // first to find the batch used up: fetch the next one
-            const unsigned long long v = atomicAdd(ticket, (unsigned long long)kBatch);
-            atomicExch(&sState, (v << 8) | 1ull);  // (ticket v + 0 is this warp's)
-            base = int(v);
-            tk = v;
-            break;
-          }
-          while ((*(volatile unsigned long long*)&sState & 0xff) >= kBatch)
-            __nanosleep(20);
-        }
-      }
-      tk = __shfl_sync(0xffffffffu, tk, 0);
-      base = __shfl_sync(0xffffffffu, base, 0);
-    } else {
-      if (lane == 0)
-        tk = atomicAdd(ticket, 1ull);
-      tk = __shfl_sync(0xffffffffu, tk, 0);
-    }
-    if (tk >= (unsigned long long)n)
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 1ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)n)
       return;
-    const int t = a.order ? a.order[tk] - a.orderBase : int(tk);
+    const int t = a.order ? a.order[base] - a.orderBase : int(base);
     const int p = a.worklist ? a.worklist[t] : 0;
-    warp_block(a, p, t, lane, batched ? sHand : nullptr, base);
+    warp_block(a, p, t, lane);
+  }
+}
+
+// A gang: several coding units (slices or frames -- independent chains with
+// their own trees, tickets and zero-run streams) in ONE launch.  A textured
+// unit is bound by the latency of its own chain and keeps only a handful of
+// warps busy, so throughput comes from the number of chains in flight; a
+// stream carries one chain, a gang launch carries as many as it has entries.
+// CTA c serves entry c % numUnits (its arguments are copied to shared memory
+// once); within a unit everything is as in k_block_warp.
+struct GangEntry {
+  WarpBlockArgs a;
+  unsigned long long* ticket;
+};
+
+__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
+k_block_warp_gang(const GangEntry* __restrict__ tab, const int numUnits)
+{
+  __shared__ GangEntry se;
+  {
+    static_assert(sizeof(GangEntry) % sizeof(uint32_t) == 0, "copied by words");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tab + blockIdx.x % numUnits);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&se);
+    for (int i = threadIdx.x; i < int(sizeof(GangEntry) / sizeof(uint32_t)); i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads();
+  const WarpBlockArgs& a = se.a;
+  unsigned long long* const ticket = se.ticket;
+  const int lane = threadIdx.x & 31;
+  const int n = *a.count;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 1ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)n)
+      return;
+    const int t = a.order ? a.order[base] - a.orderBase : int(base);
+    const int p = a.worklist ? a.worklist[t] : 0;
+    warp_block(a, p, t, lane);
   }
 }
 

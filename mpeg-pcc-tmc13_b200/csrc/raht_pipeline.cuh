@@ -38,6 +38,7 @@ namespace pccb200 {
 template<class Exec>
 struct WaveDescent {
   static constexpr bool available = false;
+  struct Job {};
 };
 
 struct StagePlan {
@@ -148,6 +149,19 @@ struct RahtSetRt {
   int* tz;  // zero-run words of the set (layout: tzOff), or null
 };
 
+// A call whose descent and tail have been prepared but not run yet: the
+// caller issues the descents of several such units together (one launch per
+// descent step for all of them, WaveDescent<Exec>::run_gang) and then
+// ex.foreach(nLeaves, tail) for each.  Only executors with their own descent
+// can defer.
+template<class Exec>
+struct RahtDeferred {
+  bool pending = false;
+  typename WaveDescent<Exec>::Job job;
+  TailFn tail;
+  int nLeaves = 0;
+};
+
 // keys / attrs / qpo / coefficients live in executor memory.  attrs: N rows of
 // all components of all sets (set 0 first), in and out.  Several sets = several
 // attributes coded on the same positions in one pass: they share the tree and
@@ -157,8 +171,11 @@ struct RahtSetRt {
 template<class Exec>
 int
 raht_run_sets(Exec& ex, const pccb200_raht_params& pp, int numSets, const RahtSetIO* io,
-              bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo, int N)
+              bool forward, const int64_t* keys, int32_t* attrs, const int32_t* qpo, int N,
+              RahtDeferred<Exec>* defer = nullptr)
 {
+  if (defer)
+    defer->pending = false;
   if (N <= 0 || numSets < 1 || numSets > 2)
     return PCCB200_ERR_INVALID_ARG;
   int A = 0;
@@ -297,7 +314,12 @@ raht_run_sets(Exec& ex, const pccb200_raht_params& pp, int numSets, const RahtSe
     bool descended = false;
     if constexpr (WaveDescent<Exec>::available) {
       if (numSets > 1 || WaveDescent<Exec>::enabled(cfg)) {
-        WaveDescent<Exec>::run(ex, cfg, numSets, rt, stages, tzOff);
+        if (defer) {
+          WaveDescent<Exec>::prepare(ex, cfg, numSets, rt, stages, tzOff, defer->job);
+          defer->pending = true;
+        } else {
+          WaveDescent<Exec>::run(ex, cfg, numSets, rt, stages, tzOff);
+        }
         descended = true;
       }
     }
@@ -364,6 +386,11 @@ raht_run_sets(Exec& ex, const pccb200_raht_params& pp, int numSets, const RahtSe
   tail.attrsOut = attrs;
   tail.coefBase = hasStages ? nLeaves : 0;
   tail.hasStages = hasStages;
+  if (defer && defer->pending) {
+    defer->tail = tail;
+    defer->nLeaves = nLeaves;
+    return PCCB200_OK;
+  }
   ex.foreach(nLeaves, tail);
   if (forward && !hasStages) {
     // all points coincide: the reference codes N-1 coefficients and no DC;

@@ -153,28 +153,108 @@ struct WaveDescent<DeviceExec> {
     return true;
   }
 
+  // Everything one unit's descent needs between its preparation (geometry,
+  // schedule: steps 1-3) and its stage launches (step 4).  Kept so that the
+  // stage launches of several units can be issued together (run_gang).
+  struct Job {
+    RahtConfig cfg;
+    int numSets = 0;
+    RahtSetRt rt[kMaxSets];
+    std::vector<Stage> stages;
+    std::vector<int64_t> tzOff;
+    int top = 0;
+    bool rdoq = false;
+    std::vector<WarpBlockArgs> args;   // one per descent step, [0] = root block
+    int rowOff[kMaxWaveSegs + 2] = {};
+    const int32_t* order = nullptr;
+    int* cntRoot = nullptr;
+    unsigned long long* tickets = nullptr;
+    TzRegion* dRegions[kMaxSets] = {nullptr, nullptr};
+  };
+
   // stages[0] = leaves ... stages.back() = children of the root block.
   // rt: the attributes coded in this pass (cfg.A = all their components);
   // rt[s].tz / tzOff: zero-run words as laid out by raht_run_sets.
   static void run(DeviceExec& ex, const RahtConfig& cfg, int numSets, const RahtSetRt* rt,
                   const std::vector<Stage>& stages, const std::vector<int64_t>& tzOff)
   {
+    Job job;
+    prepare(ex, cfg, numSets, rt, stages, tzOff, job);
+    ex.phase(kPhaseBlock);
+    for (int d = 0; d <= job.top; d++) {
+      const int nBlocks = stage_prep(ex, job, d);
+      {
+        DeviceExec::Scope sc(ex);
+        k_block_warp<<<unsigned(ex.block_grid(nBlocks)), kWarpBlockThreads, 0, ex.stream>>>(
+          job.args[d], job.tickets + d);
+        g_launchCount++;
+      }
+      PCC_CUDA_CHECK(cudaGetLastError());
+    }
+  }
+
+  // The stage launches of several prepared units, step by step: launch d
+  // carries descent step d of every unit that has one (units are independent;
+  // a step needs only the previous step of its own unit).
+  static void run_gang(DeviceExec& ex, Job* const* jobs, int numJobs)
+  {
+    int maxTop = -1;
+    for (int u = 0; u < numJobs; u++)
+      maxTop = jobs[u]->top > maxTop ? jobs[u]->top : maxTop;
+    ex.phase(kPhaseBlock);
+    std::vector<GangEntry> tab;
+    for (int d = 0; d <= maxTop; d++) {
+      tab.clear();
+      int maxBlocks = 1;
+      for (int u = 0; u < numJobs; u++) {
+        Job& job = *jobs[u];
+        if (d > job.top)
+          continue;
+        const int nBlocks = stage_prep(ex, job, d);
+        maxBlocks = nBlocks > maxBlocks ? nBlocks : maxBlocks;
+        tab.push_back(GangEntry{job.args[d], job.tickets + d});
+      }
+      const int units = int(tab.size());
+      GangEntry* dTab = ex.alloc<GangEntry>(tab.size());
+      ex.upload(dTab, tab.data(), tab.size() * sizeof(GangEntry));
+      // the lane's share of the machine, divided among the units of the gang
+      int64_t perUnit = ex.block_grid(int64_t(1) << 40) / units;
+      const int64_t useful = (int64_t(maxBlocks) + kWarpBlockThreads / 32 - 1) / (kWarpBlockThreads / 32);
+      perUnit = perUnit > useful ? useful : perUnit;
+      const char* ec = getenv("PCCB200_GANG_CTAS");  // A/B: CTAs per unit (read per call)
+      if (ec && atoi(ec) > 0 && perUnit > atoi(ec))
+        perUnit = atoi(ec);
+      perUnit = perUnit < 1 ? 1 : perUnit;
+      {
+        DeviceExec::Scope sc(ex);
+        k_block_warp_gang<<<unsigned(perUnit * units), kWarpBlockThreads, 0, ex.stream>>>(dTab, units);
+        g_launchCount++;
+      }
+      PCC_CUDA_CHECK(cudaGetLastError());
+    }
+  }
+
+  // steps 1-3 (nothing here reads an attribute value)
+  static void prepare(DeviceExec& ex, const RahtConfig& cfg, int numSets, const RahtSetRt* rt,
+                      const std::vector<Stage>& stages, const std::vector<int64_t>& tzOff, Job& job)
+  {
     const int top = int(stages.size()) - 1;
-    const int A = cfg.A;
     const bool rdoq = cfg.isEncoder && !cfg.haar;
-    static const int pollNs = [] {
-      const char* e = getenv("PCCB200_POLL_NS");
-      return e ? atoi(e) : 32;
-    }();
+    job.cfg = cfg;
+    job.numSets = numSets;
+    for (int s = 0; s < numSets; s++)
+      job.rt[s] = rt[s];
+    job.stages = stages;
+    job.tzOff = tzOff;
+    job.top = top;
+    job.rdoq = rdoq;
+    const char* ep = getenv("PCCB200_POLL_NS");  // A/B knob, read per call
+    const int pollNs = ep ? atoi(ep) : 32;
     static const bool mortonOrder = [] {  // A/B: coding order everywhere
       const char* e = getenv("PCCB200_WAVE_ORDER");
       return e && !strcmp(e, "morton");
     }();
     const bool wave = cfg.predictionEnabled && cfg.subnode && !rdoq && !mortonOrder;
-    static const int handOver = [] {  // A/B: 0 = every hand-over through L2
-      const char* e = getenv("PCCB200_HANDOVER");
-      return e ? atoi(e) : 1;
-    }();
 
     //-- row space: one segment per descent step below the root
     LevelArgs la = {};
@@ -186,6 +266,8 @@ struct WaveDescent<DeviceExec> {
     }
     la.rowOff[top + 1] = int(numRows);
     la.rowOff[0] = 0;
+    for (int d = 0; d <= top + 1; d++)
+      job.rowOff[d] = la.rowOff[d];
 
     int32_t* wl = ex.alloc<int32_t>(size_t(numRows));
     int32_t* geom = cfg.predictionEnabled ? ex.alloc<int32_t>(size_t(numRows) * kGeomStride) : nullptr;
@@ -196,6 +278,7 @@ struct WaveDescent<DeviceExec> {
     ex.zero(zero, zInts * sizeof(int));
     unsigned long long* tickets = reinterpret_cast<unsigned long long*>(zero);
     int* lv = zero + size_t(top + 2) * 2;
+    job.tickets = tickets;
 
     //-- 1. geometry, top-down
     ex.phase(kPhaseGeom);
@@ -204,15 +287,16 @@ struct WaveDescent<DeviceExec> {
       ex.foreach(1, RootQpFn{stages[top]});
     int64_t abA, abB;
     raht_ab(1, 1, abA, abB);
-    std::vector<WarpBlockArgs> args(top + 1);
+    std::vector<WarpBlockArgs>& args = job.args;
+    args.assign(top + 1, WarpBlockArgs{});
     int* cntRoot = cnt;  // cnt[0]: the root step has one block
+    job.cntRoot = cntRoot;
     {
       int one = 1;
       ex.upload(cntRoot, &one, sizeof(int));
     }
     for (int d = 0; d <= top; d++) {
       WarpBlockArgs& a = args[d];
-      a = WarpBlockArgs{};
       a.cfg = cfg;
       a.numSets = numSets;
       for (int s = 0; s < numSets; s++) {
@@ -229,7 +313,6 @@ struct WaveDescent<DeviceExec> {
       a.ab11a = abA;
       a.ab11b = abB;
       a.pollNs = pollNs;
-      a.handOver = handOver;
     }
     for (int d = 1; d <= top; d++) {
       const int si = top - d;
@@ -256,7 +339,7 @@ struct WaveDescent<DeviceExec> {
     }
 
     //-- 2 + 3. dependency levels, wavefront order
-    const int32_t* order = nullptr;
+    job.order = nullptr;
     if (wave && numRows > 0) {
       ex.phase(kPhaseOrder);
       int64_t* keyA = ex.alloc<int64_t>(size_t(numRows));
@@ -280,61 +363,60 @@ struct WaveDescent<DeviceExec> {
       int64_t* kres;
       int32_t* vres;
       device_radix_sort_pairs(ex, keyA, valA, keyB, valB, numRows, 3, &kres, &vres);
-      order = vres;
+      job.order = vres;
     }
 
-    //-- 4. the stages
-    ex.phase(kPhaseBlock);
-    TzRegion* dRegions[kMaxSets] = {nullptr, nullptr};
     if (rdoq)
       for (int s = 0; s < numSets; s++)
-        dRegions[s] = ex.alloc<TzRegion>(kMaxWaveSegs + 2);
-    for (int d = 0; d <= top; d++) {
-      const int si = top - d;
-      const Stage& S = stages[si];
-      WarpBlockArgs& a = args[d];
-      ex.fill(S.rec, 0x80, size_t(S.n) * A * sizeof(int64_t));
-      int nBlocks = 1;
-      if (d == 0) {
-        a.S = S;
-        a.P = Stage{};
-        a.P.n = 0;
-        a.coefBase = 0;
-        a.predInLvl = 0;
-        a.worklist = nullptr;
-        a.geom = nullptr;
-        a.count = cntRoot;
-      } else {
-        const Stage& P = stages[si + 1];
-        nBlocks = P.n;
-        ex.foreach(nBlocks, PrepFn{cfg, S, P, cfg.predictionEnabled, nullptr, 2});
-        a.order = order ? order + la.rowOff[d] : nullptr;
-        a.orderBase = la.rowOff[d];
-      }
-      a.stageIdx = d;
-      for (int s = 0; s < numSets; s++) {
-        AttrSet& st = a.set[s];
-        st.qpLayer = d + 1 < rt[s].numLayers ? d + 1 : rt[s].numLayers - 1;
-        st.acLayer = d;
-        if (rdoq) {
-          TzRegion hr;
-          hr.words = rt[s].tz + tzOff[si];
-          hr.lists = ex.alloc<int>((size_t(nBlocks) + 1) * 2);
-          hr.count = a.count;
-          ex.upload(dRegions[s] + d, &hr, sizeof(TzRegion));
-          st.regions = dRegions[s];
-          st.words = hr.words;
-          st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
-        }
-      }
-      {
-        DeviceExec::Scope sc(ex);
-        k_block_warp<<<unsigned(ex.block_grid(nBlocks)), kWarpBlockThreads, 0, ex.stream>>>(
-          a, tickets + d);
-        g_launchCount++;
-      }
-      PCC_CUDA_CHECK(cudaGetLastError());
+        job.dRegions[s] = ex.alloc<TzRegion>(kMaxWaveSegs + 2);
+    PCC_CUDA_CHECK(cudaGetLastError());
+  }
+
+  //-- 4. what precedes the block kernel of descent step d: reconstruction
+  //   slots armed, single-child blocks passed through (they read the previous
+  //   step's results), the step's zero-run region.  Returns its block count.
+  static int stage_prep(DeviceExec& ex, Job& job, int d)
+  {
+    const RahtConfig& cfg = job.cfg;
+    const int top = job.top;
+    const int si = top - d;
+    const Stage& S = job.stages[si];
+    WarpBlockArgs& a = job.args[d];
+    ex.fill(S.rec, 0x80, size_t(S.n) * cfg.A * sizeof(int64_t));
+    int nBlocks = 1;
+    if (d == 0) {
+      a.S = S;
+      a.P = Stage{};
+      a.P.n = 0;
+      a.coefBase = 0;
+      a.predInLvl = 0;
+      a.worklist = nullptr;
+      a.geom = nullptr;
+      a.count = job.cntRoot;
+    } else {
+      const Stage& P = job.stages[si + 1];
+      nBlocks = P.n;
+      ex.foreach(nBlocks, PrepFn{cfg, S, P, cfg.predictionEnabled, nullptr, 2});
+      a.order = job.order ? job.order + job.rowOff[d] : nullptr;
+      a.orderBase = job.rowOff[d];
     }
+    a.stageIdx = d;
+    for (int s = 0; s < job.numSets; s++) {
+      AttrSet& st = a.set[s];
+      st.qpLayer = d + 1 < job.rt[s].numLayers ? d + 1 : job.rt[s].numLayers - 1;
+      st.acLayer = d;
+      if (job.rdoq) {
+        TzRegion hr;
+        hr.words = job.rt[s].tz + job.tzOff[si];
+        hr.lists = ex.alloc<int>((size_t(nBlocks) + 1) * 2);
+        hr.count = a.count;
+        ex.upload(job.dRegions[s] + d, &hr, sizeof(TzRegion));
+        st.regions = job.dRegions[s];
+        st.words = hr.words;
+        st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+      }
+    }
+    return nBlocks;
   }
 };
 

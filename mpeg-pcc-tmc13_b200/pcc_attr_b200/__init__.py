@@ -81,9 +81,11 @@ EXPORTS = [
     "pccb200_abi_version", "pccb200_attr_lift_decode", "pccb200_attr_lift_decode_lod",
     "pccb200_attr_lift_decode_slices", "pccb200_attr_lift_encode", "pccb200_attr_lift_encode_lod",
     "pccb200_attr_lift_encode_slices", "pccb200_attr_raht_decode",
-    "pccb200_attr_raht_decode_multi", "pccb200_attr_raht_decode_multi_dev",
+    "pccb200_attr_raht_decode_multi", "pccb200_attr_raht_decode_multi_batch",
+    "pccb200_attr_raht_decode_multi_batch_dev", "pccb200_attr_raht_decode_multi_dev",
     "pccb200_attr_raht_decode_slices_dev", "pccb200_attr_raht_encode",
-    "pccb200_attr_raht_encode_multi", "pccb200_attr_raht_encode_multi_dev",
+    "pccb200_attr_raht_encode_multi", "pccb200_attr_raht_encode_multi_batch",
+    "pccb200_attr_raht_encode_multi_batch_dev", "pccb200_attr_raht_encode_multi_dev",
     "pccb200_attr_raht_encode_slices", "pccb200_attr_raht_encode_slices_dev",
     "pccb200_attr_raht_encode_symbols", "pccb200_attr_spherical_positions",
     "pccb200_coeff_symbols", "pccb200_estimate_dist2", "pccb200_kernel_launch_count",
@@ -289,6 +291,78 @@ def attr_raht_encode_multi_dev(params, qpsets, d_xyz, d_attrs, d_coefs, n, num_a
     bd = (C.c_int32 * k)(*bitdepths)
     _check(lib().pccb200_attr_raht_encode_multi_dev(
         C.byref(params), C.c_int32(k), qp, C.c_void_p(d_xyz), at, na, bd, C.c_int32(n), co))
+
+
+def _batch_args(qpsets, units_attrs, units_coefs, bitdepths):
+    k = len(qpsets)
+    m = len(units_attrs)
+    QP = C.POINTER(QpSet) * k
+    VP = C.c_void_p * (m * k)
+    qp = QP(*[C.pointer(q) for q in qpsets])
+
+    def ptr(x):
+        return x if isinstance(x, int) else x.ctypes.data
+
+    at = VP(*[ptr(a) for u in units_attrs for a in u])
+    co = VP(*[ptr(c) for u in units_coefs for c in u])
+    bd = (C.c_int32 * k)(*bitdepths)
+    return qp, at, co, bd
+
+
+def attr_raht_encode_multi_batch_into(params, qpsets, xyzs, attrs_inout, coeffs_out, bitdepths=None):
+    """Many coding units (slices / frames) in one call, zero-copy form.
+    xyzs[u]: [N_u, 3] int32; attrs_inout[u][s]: [N_u, A_s] int32 (overwritten
+    with the reconstruction); coeffs_out[u][s]: [A_s, N_u] int32."""
+    k = len(qpsets)
+    m = len(xyzs)
+    bitdepths = bitdepths or [8] * k
+    qp, at, co, bd = _batch_args(qpsets, attrs_inout, coeffs_out, bitdepths)
+    na = (C.c_int32 * k)(*[int(a.shape[1]) for a in attrs_inout[0]])
+    xp = (C.c_void_p * m)(*[x.ctypes.data for x in xyzs])
+    ns = (C.c_int32 * m)(*[int(x.shape[0]) for x in xyzs])
+    _check(lib().pccb200_attr_raht_encode_multi_batch(
+        C.byref(params), C.c_int32(k), qp, C.c_int32(m), xp, at, na, bd, ns, co))
+
+
+def attr_raht_encode_multi_batch(params, qpsets, xyzs, attrs, bitdepths=None):
+    """-> (recs[u][s], coefs[u][s])"""
+    xyzs = [np.ascontiguousarray(x, dtype=np.int32) for x in xyzs]
+    a = [[np.ascontiguousarray(x, dtype=np.int32).copy() for x in u] for u in attrs]
+    c = [[np.empty((x.shape[1], x.shape[0]), dtype=np.int32) for x in u] for u in a]
+    attr_raht_encode_multi_batch_into(params, qpsets, xyzs, a, c, bitdepths)
+    return a, c
+
+
+def attr_raht_decode_multi_batch(params, qpsets, xyzs, coeffs, bitdepths=None):
+    """-> recs[u][s]"""
+    k = len(qpsets)
+    m = len(xyzs)
+    bitdepths = bitdepths or [8] * k
+    xyzs = [np.ascontiguousarray(x, dtype=np.int32) for x in xyzs]
+    c = [[np.ascontiguousarray(x, dtype=np.int32) for x in u] for u in coeffs]
+    a = [[np.empty((x.shape[1], x.shape[0]), dtype=np.int32) for x in u] for u in c]
+    qp, at, co, bd = _batch_args(qpsets, a, c, bitdepths)
+    na = (C.c_int32 * k)(*[int(x.shape[1]) for x in a[0]])
+    xp = (C.c_void_p * m)(*[x.ctypes.data for x in xyzs])
+    ns = (C.c_int32 * m)(*[int(x.shape[0]) for x in xyzs])
+    _check(lib().pccb200_attr_raht_decode_multi_batch(
+        C.byref(params), C.c_int32(k), qp, C.c_int32(m), xp, at, na, bd, ns, co))
+    return a
+
+
+def attr_raht_multi_batch_dev(forward, params, qpsets, d_xyzs, d_attrs, d_coefs, ns, num_attrs,
+                              bitdepths=None):
+    """device pointers (ints): d_xyzs[u], d_attrs[u][s], d_coefs[u][s]; ns[u] points"""
+    k = len(qpsets)
+    m = len(d_xyzs)
+    bitdepths = bitdepths or [8] * k
+    qp, at, co, bd = _batch_args(qpsets, d_attrs, d_coefs, bitdepths)
+    na = (C.c_int32 * k)(*num_attrs)
+    xp = (C.c_void_p * m)(*d_xyzs)
+    nn = (C.c_int32 * m)(*ns)
+    fn = (lib().pccb200_attr_raht_encode_multi_batch_dev if forward
+          else lib().pccb200_attr_raht_decode_multi_batch_dev)
+    _check(fn(C.byref(params), C.c_int32(k), qp, C.c_int32(m), xp, at, na, bd, nn, co))
 
 
 def quant_weights(preds, num_points_in_lod):

@@ -238,6 +238,54 @@ def test_multi_attribute_pass(b200, case):
         assert np.array_equal(dec[s], recs[s]), (case, s)
 
 
+@pytest.mark.parametrize("case", ["enc_rgb_refl", "haar", "one_set", "aclayers"])
+def test_multi_batch_gang(b200, case):
+    """Many units (slices / frames) in one call: the top-down passes of the
+    units of a gang share their launches (k_block_warp_gang).  Units of
+    different sizes and depths, against the oracle run per unit and attribute;
+    decoder through the same entry."""
+    from pcc_attr_b200.synth import texture
+
+    kw, q1kw, q2kw = {}, dict(qp=34), dict(qp=28, chroma_offset=0)
+    if case == "haar":
+        kw = dict(haar=1)
+    elif case == "aclayers":  # no fused path: unit by unit internally
+        q1kw = dict(qp=34, ac_qps=[[(c % 3 - 1, (c + 1) % 3 - 1) for c in range(7)], [(1, 0)] * 7])
+    units = []
+    for u, (n, bits) in enumerate([(30000, 9), (2000, 7), (70000, 10), (9, 4), (45000, 9),
+                                   (120000, 11), (15000, 8)]):
+        if u % 2:
+            xyz, rgb = cloud_lidar(n, seed=40 + u)
+        else:
+            xyz, rgb = cloud_shell(n, bits=bits, seed=40 + u, dups=(u == 4))
+        rgb = texture(rgb, 20, 3 + u)
+        refl = texture(((rgb[:, :1] * 2 + rgb[:, 2:3]) // 3).astype(np.int32), 12, 6 + u)
+        units.append((xyz, [rgb, refl] if case != "one_set" else [rgb]))
+    params = make_params(search_range=500, **kw)
+    qs = [make_qpset(**q1kw), make_qpset(**q2kw)]
+    if case == "one_set":
+        qs = qs[:1]
+    p = b200.RahtParams.from_buffer_copy(bytes(params))
+    q = [b200.QpSet.from_buffer_copy(bytes(x)) for x in qs]
+    for gang in ("0", "3"):  # spread over the lanes / gangs of three
+        os.environ["PCCB200_GANG"] = gang
+        recs, coefs = b200.attr_raht_encode_multi_batch(
+            p, q, [x for x, _ in units], [a for _, a in units])
+        for u, (xyz, attrs) in enumerate(units):
+            for s, at in enumerate(attrs):
+                mort, a_s, order = sort_cloud(xyz, at)
+                orec, ocoef = oracle_raht(1, params, qs[s], mort, a_s)
+                exp = np.empty_like(orec)
+                exp[order] = np.clip(orec, 0, 255)
+                assert np.array_equal(coefs[u][s], ocoef), (case, gang, u, s)
+                assert np.array_equal(recs[u][s], exp), (case, gang, u, s)
+        dec = b200.attr_raht_decode_multi_batch(p, q, [x for x, _ in units], coefs)
+        for u in range(len(units)):
+            for s in range(len(qs)):
+                assert np.array_equal(dec[u][s], recs[u][s]), (case, gang, u, s)
+    del os.environ["PCCB200_GANG"]
+
+
 @pytest.mark.parametrize("a", [1, 3])
 def test_lifting_vs_oracle(b200, a):
     """quantisation weights and forward / inverse lifting (64-bit atomics per
