@@ -61,6 +61,7 @@ struct WarpBlockArgs {
   // order[i] (worklist rank + orderBase), rows sorted by dependency level
   const int32_t* order;
   int orderBase;
+  int chunked;  // coding order: chunks of tickets per CTA, hand-over through shared memory
 };
 
 // Zero-run bookkeeping of one stage, indexed by worklist rank t:
@@ -214,6 +215,35 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
   return kCodeHard;
 }
 
+// Hand-over through shared memory.  In coding order a CTA takes its tickets a
+// chunk of kChunk consecutive tickets at a time and deals them to its warps
+// round robin (ticket base + i runs on warp i % 8), so a chain of adjacent
+// blocks stays inside the CTA for kChunk hops: what a block hands to the blocks
+// after it -- the reconstruction of its children, its zero-run words -- goes
+// through one slot per ticket of the chunk as well as through L2, and the
+// consumer, which is on the critical path of the whole stage, spins on shared
+// memory instead of paying L2 round trips.  The CTA finishes a chunk (barrier)
+// before it claims the next one: a slot belongs to one ticket for the whole
+// chunk, so a reader never has to validate what it read; slots carry the full
+// ticket number, stale content of the previous chunk just reads as "not yet".
+// Deadlock freedom is as before: chunks are claimed in ascending order by
+// running CTAs, a warp works through its tickets of a chunk in ascending order
+// and a block waits for lower tickets only.
+constexpr int kChunk = 64;
+struct ChainSlot {
+  unsigned long long w[kMaxSets];     // (ticket + 1) << 32 | zero-run word of the set
+  unsigned long long list[kMaxSets];  // classification list (valid once the word says so)
+  int tag;                            // ticket whose rec[] is complete
+  int pad;
+  long long rec[32];                  // reconstruction by lane (component row * 8 + child slot)
+};
+
+__device__ __forceinline__ unsigned long long
+slot_word(int t, int w)
+{
+  return (unsigned long long)(unsigned(t + 1)) << 32 | unsigned(w);
+}
+
 // Is the run of non-resetting coefficients that ends just before block t of
 // stage a.stageIdx at least `need` long?  Walks back over the published
 // classification of earlier blocks (this stage, then earlier stages); waits
@@ -232,7 +262,8 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 // around the poll makes every waiting warp more expensive.
 __device__ __forceinline__ bool
 tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, int need,
-                const int wPre1, const int wPre2)
+                const int wPre1, const int wPre2, volatile ChainSlot* hs, const int chunkBase,
+                const int si)
 {
   if (need <= 0)
     return true;
@@ -252,19 +283,37 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
       u = *rg.count - 1;
       continue;
     }
-    // (words fetched ahead are as good as fresh ones unless they were empty)
-    int w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
-    while (tz_status(w) == kTzNone) {
-      w = ld_acquire(&words[u + 1]);
-      if (tz_status(w) != kTzNone)
-        break;
-      __nanosleep(pollNs);
+    int w = 0;
+    unsigned long long L = 0;
+    if (hs && s == stageIdx && u >= chunkBase) {
+      // a block of this CTA's chunk: its words are in its slot
+      volatile ChainSlot* h = &hs[u - chunkBase];
+      unsigned long long v64 = h->w[si];
+      while (unsigned(v64 >> 32) != unsigned(u + 1) || tz_status(int(unsigned(v64))) == kTzNone) {
+        __nanosleep(20);
+        v64 = h->w[si];
+      }
+      w = int(unsigned(v64));
+      if (tz_status(w) == kTzClassified) {
+        __threadfence_block();
+        L = h->list[si];
+      }
+    } else {
+      // (words fetched ahead are as good as fresh ones unless they were empty)
+      w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
+      while (tz_status(w) == kTzNone) {
+        w = ld_acquire(&words[u + 1]);
+        if (tz_status(w) != kTzNone)
+          break;
+        __nanosleep(pollNs);
+      }
+      if (tz_status(w) == kTzClassified)
+        L = lists[u + 1];
     }
     const int st_ = tz_status(w), v = tz_value(w);
     if (st_ == kTzExit)
       return v + acc >= req;
     if (st_ == kTzClassified) {
-      const unsigned long long L = lists[u + 1];
       for (int i = v - 1; i >= 0; i--) {
         const int pos = acc + (v - i);
         if (pos > req)
@@ -293,7 +342,8 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
 // quantisers, the inherited DC), do all the arithmetic that needs only those,
 // and only then look at the values still being produced.
 __device__ __forceinline__ void
-warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
+warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
+           volatile ChainSlot* hs, const int chunkBase)
 {
   const RahtConfig& cfg = a.cfg;
   const Stage& S = a.S;
@@ -316,6 +366,21 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   const bool ext = cfg.ext != 0;
   const bool enc = cfg.isEncoder != 0;
   const bool rdoq = enc && !haar;
+
+  // this block's slot; the blocks of the (up to 31) tickets before it in the
+  // chunk, one per lane: the likely producers of what it will wait for
+  volatile ChainSlot* me = hs ? &hs[t - chunkBase] : nullptr;
+  int prevBlock = -1;
+  if (hs) {
+    if (lane == 0) {
+      me->tag = -1;
+      me->w[0] = slot_word(t, 0);
+      me->w[1] = slot_word(t, 0);
+    }
+    if (lane >= 1 && t - lane >= chunkBase)
+      prevBlock = a.worklist[t - lane];
+    __syncwarp();
+  }
 
   const int c0 = root ? 0 : P.first[p];
   uint32_t occ;
@@ -531,6 +596,20 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     // loads of up to four neighbours go out together, then whatever has not
     // been produced yet is polled
     uint32_t cm = childNb;
+    // neighbours whose block is one of the previous tickets of the chunk: bit
+    // i of localNb, the producing ticket is t - localDist (per neighbour)
+    uint32_t localNb = 0;
+    if (hs) {
+      uint32_t c2 = cm;
+      while (c2) {
+        const int i = __ffs(c2) - 1;
+        c2 &= c2 - 1;
+        const int qi = __shfl_sync(0xffffffffu, nq, i);
+        if (__ballot_sync(0xffffffffu, prevBlock == qi))
+          localNb |= 1u << i;
+      }
+      cm &= ~localNb;
+    }
     while (cm) {
       int64_t v[4];
       const int64_t* ad[4];
@@ -576,6 +655,39 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       for (int u = 0; u < 4; u++)
         pred += v[u] * (wc[u] * fracMul);
     }
+    // the neighbours of this chunk last (they are the ones still being
+    // produced), oldest first: through shared memory
+    while (localNb) {
+      // the one produced by the lowest ticket first
+      int best = -1, bestDist = 0;
+      uint32_t c2 = localNb;
+      while (c2) {
+        const int i = __ffs(c2) - 1;
+        c2 &= c2 - 1;
+        const int qi = __shfl_sync(0xffffffffu, nq, i);
+        const int dist = __ffs(__ballot_sync(0xffffffffu, prevBlock == qi)) - 1;
+        if (dist > bestDist) {
+          bestDist = dist;
+          best = i;
+        }
+      }
+      const int i = best;
+      localNb &= ~(1u << i);
+      const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
+      const int ii = i - 7;
+      const int sh = occu_shift(ii);
+      const int shift = ii < 9 ? sh : -sh;
+      const uint32_t cmask =
+        (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
+      const bool need = act && ((cmask >> j) & 1) && ((validMask >> i) & 1);
+      const int r = t - bestDist;
+      volatile ChainSlot* h = &hs[r - chunkBase];
+      while (h->tag != r)
+        __nanosleep(20);
+      __threadfence_block();
+      if (need)
+        pred += int64_t(h->rec[(j + shift) + 8 * k]) * (cfg.predWeightChild[ii] * fracMul);
+    }
     if (present && act) {
       int64_t v = fx_mul(pred, div);
       if (haar)
@@ -597,10 +709,10 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   // overlaps the arithmetic up to the block's own classification instead of
   // following it.
   int wPre1 = 0, wPre2 = 0;
-  if (rdoq && act) {
-    if (t >= 1)
+  if (rdoq && act) {  // (inside the chunk the words come from the slots)
+    if (t >= 1 && !(hs && t - 1 >= chunkBase))
       wPre1 = ld_acquire(&my.words[t]);
-    if (t >= 2)
+    if (t >= 2 && !(hs && t - 2 >= chunkBase))
       wPre2 = ld_acquire(&my.words[t - 1]);
   }
 
@@ -682,12 +794,23 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         prev = m + 1;
       }
       e += ncoef - prev;
-      if (speaker)
+      if (speaker) {
+        if (me)
+          me->w[si] = slot_word(t, tz_pack(kTzExit, e));
         st_release(&my.words[t + 1], tz_pack(kTzExit, e));
+      }
     } else if (!hasS) {
-      if (speaker)
+      if (speaker) {
+        if (me)
+          me->w[si] = slot_word(t, tz_pack(kTzTransparent, ncoef));
         st_release(&my.words[t + 1], tz_pack(kTzTransparent, ncoef));
+      }
     } else if (speaker) {
+      if (me) {
+        me->list[si] = codes;
+        __threadfence_block();
+        me->w[si] = slot_word(t, tz_pack(kTzClassified, ncoef));
+      }
       my.lists[t + 1] = codes;
       st_release(&my.words[t + 1], tz_pack(kTzClassified, ncoef));
     }
@@ -713,7 +836,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
         if ((softM >> m) & 1) {
           const int th = thr_decode(int((codes >> (6 * m)) & 63));
           if (linked)
-            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2);
+            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2, hs, chunkBase, si);
           else
             f = tl >= th;
         }
@@ -731,9 +854,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
           flagMine = f;
       }
       tl += ncoef - prev;
-      if (!hasH && speaker)
-        st_release(&my.words[t + 1],
-                   linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl));
+      if (!hasH && speaker) {
+        const int fw = linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl);
+        if (me)
+          me->w[si] = slot_word(t, fw);
+        st_release(&my.words[t + 1], fw);
+      }
     }
   }
 
@@ -756,12 +882,24 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
 #pragma unroll
   for (int s = 2; s >= 0; s--)
     pred = bfly_inv(pred, bf[s], 1 << s, haar);
+  int64_t recOut = 0;
   if (present && act) {
     int64_t v = pred;
-    S.recUs[size_t(cidx) * A + k] = ext ? v : fx_round(v * 4);
     if (rsMul)
       v = fx_mul(v >> rsShift, rsMul);
-    st_rec(&S.rec[size_t(cidx) * A + k], ext ? v : fx_round(v));
+    recOut = ext ? v : fx_round(v);
+  }
+  if (me) {  // first where the next block of the chain looks first
+    me->rec[lane] = recOut;
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      me->tag = t;
+    }
+  }
+  if (present && act) {
+    st_rec(&S.rec[size_t(cidx) * A + k], recOut);
+    S.recUs[size_t(cidx) * A + k] = ext ? pred : fx_round(pred * 4);
   }
 }
 
@@ -821,22 +959,65 @@ k_block_geom(const WarpBlockArgs a)
 // (Morton = coding order) or, with a wavefront schedule, entry order[i].  Either
 // way everything a block may wait for has a lower ticket, i.e. is owned by a
 // running warp.
-__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
-k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
+// the ticket loop of one CTA (shared by the single-unit and the gang kernel)
+__device__ __forceinline__ void
+block_ticket_loop(const WarpBlockArgs& a, unsigned long long* ticket, ChainSlot* slots,
+                  unsigned long long* sBase)
 {
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
+  // coding order over a worklist: chunks of tickets, hand-over through shared memory
+  const bool chunked = a.order == nullptr && a.worklist != nullptr && a.chunked;
+  const int warp = threadIdx.x >> 5;
+  const int numWarps = blockDim.x >> 5;
+  if (chunked)
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
+      slots[i].tag = -1;
+      slots[i].w[0] = 0;
+      slots[i].w[1] = 0;
+    }
+  int cur = 0, end = 0, chunkBase = 0;  // chunked: this warp's next ticket, the chunk's end
+  bool inChunk = false;
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0)
-      base = atomicAdd(ticket, 1ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned long long)n)
-      return;
-    const int t = a.order ? a.order[base] - a.orderBase : int(base);
+    int t;
+    if (chunked) {
+      if (cur >= end) {
+        if (inChunk)
+          __syncthreads();  // the chunk is done: its slots and *sBase may be reused
+        if (threadIdx.x == 0)
+          *sBase = atomicAdd(ticket, (unsigned long long)kChunk);
+        __syncthreads();
+        const unsigned long long base = *sBase;
+        if (base >= (unsigned long long)n)
+          return;
+        inChunk = true;
+        chunkBase = int(base);
+        end = chunkBase + kChunk < n ? chunkBase + kChunk : n;
+        cur = chunkBase + warp;
+        continue;
+      }
+      t = cur;
+      cur += numWarps;
+    } else {
+      unsigned long long base = 0;
+      if (lane == 0)
+        base = atomicAdd(ticket, 1ull);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= (unsigned long long)n)
+        return;
+      t = a.order ? a.order[base] - a.orderBase : int(base);
+    }
     const int p = a.worklist ? a.worklist[t] : 0;
-    warp_block(a, p, t, lane);
+    warp_block(a, p, t, lane, chunked ? slots : nullptr, chunkBase);
   }
+}
+
+__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
+k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
+{
+  __shared__ ChainSlot sSlots[kChunk];
+  __shared__ unsigned long long sBase;
+  block_ticket_loop(a, ticket, sSlots, &sBase);
 }
 
 // A gang: several coding units (slices or frames -- independent chains with
@@ -863,21 +1044,9 @@ k_block_warp_gang(const GangEntry* __restrict__ tab, const int numUnits)
       dst[i] = src[i];
   }
   __syncthreads();
-  const WarpBlockArgs& a = se.a;
-  unsigned long long* const ticket = se.ticket;
-  const int lane = threadIdx.x & 31;
-  const int n = *a.count;
-  for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0)
-      base = atomicAdd(ticket, 1ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned long long)n)
-      return;
-    const int t = a.order ? a.order[base] - a.orderBase : int(base);
-    const int p = a.worklist ? a.worklist[t] : 0;
-    warp_block(a, p, t, lane);
-  }
+  __shared__ ChainSlot sSlots[kChunk];
+  __shared__ unsigned long long sBase;
+  block_ticket_loop(se.a, se.ticket, sSlots, &sBase);
 }
 
 __device__ __forceinline__ int

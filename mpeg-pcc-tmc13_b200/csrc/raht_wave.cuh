@@ -250,6 +250,8 @@ struct WaveDescent<DeviceExec> {
     job.rdoq = rdoq;
     const char* ep = getenv("PCCB200_POLL_NS");  // A/B knob, read per call
     const int pollNs = ep ? atoi(ep) : 32;
+    const char* ech = getenv("PCCB200_CHUNKED");  // A/B: 0 = every hand-over through L2
+    const int chunked = ech ? atoi(ech) : 1;
     static const bool mortonOrder = [] {  // A/B: coding order everywhere
       const char* e = getenv("PCCB200_WAVE_ORDER");
       return e && !strcmp(e, "morton");
@@ -313,6 +315,7 @@ struct WaveDescent<DeviceExec> {
       a.ab11a = abA;
       a.ab11b = abB;
       a.pollNs = pollNs;
+      a.chunked = chunked;
     }
     for (int d = 1; d <= top; d++) {
       const int si = top - d;

@@ -301,7 +301,7 @@ def _batch_args(qpsets, units_attrs, units_coefs, bitdepths):
     qp = QP(*[C.pointer(q) for q in qpsets])
 
     def ptr(x):
-        return x if isinstance(x, int) else x.ctypes.data
+        return x if isinstance(x, int) else x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
 
     at = VP(*[ptr(a) for u in units_attrs for a in u])
     co = VP(*[ptr(c) for u in units_coefs for c in u])
@@ -318,7 +318,7 @@ def attr_raht_encode_multi_batch_into(params, qpsets, xyzs, attrs_inout, coeffs_
     bitdepths = bitdepths or [8] * k
     qp, at, co, bd = _batch_args(qpsets, attrs_inout, coeffs_out, bitdepths)
     na = (C.c_int32 * k)(*[int(a.shape[1]) for a in attrs_inout[0]])
-    xp = (C.c_void_p * m)(*[x.ctypes.data for x in xyzs])
+    xp = (C.c_void_p * m)(*[x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data for x in xyzs])
     ns = (C.c_int32 * m)(*[int(x.shape[0]) for x in xyzs])
     _check(lib().pccb200_attr_raht_encode_multi_batch(
         C.byref(params), C.c_int32(k), qp, C.c_int32(m), xp, at, na, bd, ns, co))
