@@ -61,7 +61,6 @@ struct WarpBlockArgs {
   // order[i] (worklist rank + orderBase), rows sorted by dependency level
   const int32_t* order;
   int orderBase;
-  int chunked;  // coding order: chunks of tickets per CTA, hand-over through shared memory
 };
 
 // Zero-run bookkeeping of one stage, indexed by worklist rank t:
@@ -215,28 +214,28 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
   return kCodeHard;
 }
 
-// Hand-over through shared memory.  In coding order a CTA takes its tickets a
-// chunk of kChunk consecutive tickets at a time and deals them to its warps
-// round robin (ticket base + i runs on warp i % 8), so a chain of adjacent
-// blocks stays inside the CTA for kChunk hops: what a block hands to the blocks
-// after it -- the reconstruction of its children, its zero-run words -- goes
-// through one slot per ticket of the chunk as well as through L2, and the
-// consumer, which is on the critical path of the whole stage, spins on shared
-// memory instead of paying L2 round trips.  The CTA finishes a chunk (barrier)
-// before it claims the next one: a slot belongs to one ticket for the whole
-// chunk, so a reader never has to validate what it read; slots carry the full
-// ticket number, stale content of the previous chunk just reads as "not yet".
-// Deadlock freedom is as before: chunks are claimed in ascending order by
-// running CTAs, a warp works through its tickets of a chunk in ascending order
-// and a block waits for lower tickets only.
-constexpr int kChunk = 64;
+// Hand-over through shared memory (the chain kernel, k_block_chain_gang).  A
+// unit whose blocks form one chain is served by ONE CTA: ticket t runs on warp
+// t % W, every warp works through its tickets in ascending order (no atomics;
+// a block waits for lower tickets only, and the lowest unfinished ticket is
+// always the current one of its warp: no deadlock).  What a block hands to the
+// blocks after it -- the reconstruction of its children, its zero-run words --
+// goes through a ring of slots (slot t % R, R = 4 W: a warp reuses its own
+// slots only) as well as through L2, and the consumer, which is on the critical
+// path of the whole stage, spins on shared memory instead of paying L2 round
+// trips.  Slots carry the full ticket number: a reader that finds an older
+// ticket waits, one that finds a later ticket (the slot has moved on) takes the
+// value from global memory, where everything is published as before; reads of
+// more than one word are validated after the fact (the owner invalidates the
+// slot before it writes anything of its next ticket).
 struct ChainSlot {
   unsigned long long w[kMaxSets];     // (ticket + 1) << 32 | zero-run word of the set
   unsigned long long list[kMaxSets];  // classification list (valid once the word says so)
-  int tag;                            // ticket whose rec[] is complete
+  int tag;                            // ticket whose rec[] is complete, -1 while it is rewritten
   int pad;
   long long rec[32];                  // reconstruction by lane (component row * 8 + child slot)
 };
+constexpr int kChainLookBack = 31;  // tickets behind a block that are looked for in the ring
 
 __device__ __forceinline__ unsigned long long
 slot_word(int t, int w)
@@ -263,7 +262,7 @@ slot_word(int t, int w)
 __device__ __forceinline__ bool
 tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, int need,
                 const int wPre1, const int wPre2, volatile ChainSlot* hs, const int chunkBase,
-                const int si)
+                const int ringSize, const int si)
 {
   if (need <= 0)
     return true;
@@ -285,20 +284,32 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
     }
     int w = 0;
     unsigned long long L = 0;
+    bool fromRing = false;
     if (hs && s == stageIdx && u >= chunkBase) {
-      // a block of this CTA's chunk: its words are in its slot
-      volatile ChainSlot* h = &hs[u - chunkBase];
-      unsigned long long v64 = h->w[si];
-      while (unsigned(v64 >> 32) != unsigned(u + 1) || tz_status(int(unsigned(v64))) == kTzNone) {
+      // a recent block of this CTA: its words are in its slot (unless the slot
+      // has moved on, which means they have long been in global memory)
+      volatile ChainSlot* h = &hs[u % ringSize];
+      for (;;) {
+        const unsigned long long v64 = h->w[si];
+        const unsigned hi = unsigned(v64 >> 32);
+        if (hi > unsigned(u + 1))
+          break;
+        if (hi == unsigned(u + 1) && tz_status(int(unsigned(v64))) != kTzNone) {
+          w = int(unsigned(v64));
+          fromRing = true;
+          if (tz_status(w) == kTzClassified) {
+            __threadfence_block();
+            L = h->list[si];
+            __threadfence_block();
+            fromRing = unsigned(h->w[si] >> 32) == unsigned(u + 1);
+          }
+          break;
+        }
         __nanosleep(20);
-        v64 = h->w[si];
       }
-      w = int(unsigned(v64));
-      if (tz_status(w) == kTzClassified) {
-        __threadfence_block();
-        L = h->list[si];
-      }
-    } else {
+    }
+    if (!fromRing) {
+      w = 0;
       // (words fetched ahead are as good as fresh ones unless they were empty)
       w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
       while (tz_status(w) == kTzNone) {
@@ -343,7 +354,7 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
 // and only then look at the values still being produced.
 __device__ __forceinline__ void
 warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
-           volatile ChainSlot* hs, const int chunkBase)
+           volatile ChainSlot* hs, const int ringSize)
 {
   const RahtConfig& cfg = a.cfg;
   const Stage& S = a.S;
@@ -367,17 +378,20 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
   const bool enc = cfg.isEncoder != 0;
   const bool rdoq = enc && !haar;
 
-  // this block's slot; the blocks of the (up to 31) tickets before it in the
-  // chunk, one per lane: the likely producers of what it will wait for
-  volatile ChainSlot* me = hs ? &hs[t - chunkBase] : nullptr;
+  // this block's slot; the blocks of the (up to 31) tickets before it, one per
+  // lane: the likely producers of what it will wait for
+  volatile ChainSlot* me = hs ? &hs[t % ringSize] : nullptr;
+  const int chunkBase = t > kChainLookBack ? t - kChainLookBack : 0;  // oldest ticket looked for in the ring
   int prevBlock = -1;
   if (hs) {
     if (lane == 0) {
       me->tag = -1;
+      __threadfence_block();
       me->w[0] = slot_word(t, 0);
       me->w[1] = slot_word(t, 0);
+      __threadfence_block();
     }
-    if (lane >= 1 && t - lane >= chunkBase)
+    if (lane >= 1 && t - lane >= 0)
       prevBlock = a.worklist[t - lane];
     __syncwarp();
   }
@@ -674,6 +688,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
       const int i = best;
       localNb &= ~(1u << i);
       const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
+      const int cfirst = __shfl_sync(0xffffffffu, nfirst, i);
       const int ii = i - 7;
       const int sh = occu_shift(ii);
       const int shift = ii < 9 ? sh : -sh;
@@ -681,12 +696,33 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
       const bool need = act && ((cmask >> j) & 1) && ((validMask >> i) & 1);
       const int r = t - bestDist;
-      volatile ChainSlot* h = &hs[r - chunkBase];
-      while (h->tag != r)
+      volatile ChainSlot* h = &hs[r % ringSize];
+      int64_t val = 0;
+      bool got = false;
+      for (;;) {
+        if (h->tag == r) {
+          __threadfence_block();
+          val = need ? int64_t(h->rec[(j + shift) + 8 * k]) : 0;
+          __threadfence_block();
+          got = h->tag == r;  // still that block's slot: the values are its own
+          break;
+        }
+        if (unsigned(h->w[0] >> 32) > unsigned(r + 1))
+          break;  // the slot has moved on: the values are in global memory by now
         __nanosleep(20);
-      __threadfence_block();
+      }
+      if (!__all_sync(0xffffffffu, got)) {
+        const int c = cfirst + __popc(no & ((1u << (j + shift)) - 1));
+        const int64_t* ad1 = need ? &S.rec[size_t(c) * A + k] : nullptr;
+        val = ad1 ? ld_rec(ad1) : 0;
+        while (__any_sync(0xffffffffu, ad1 && val == kRecNotReady)) {
+          __nanosleep(a.pollNs);
+          if (ad1 && val == kRecNotReady)
+            val = ld_rec(ad1);
+        }
+      }
       if (need)
-        pred += int64_t(h->rec[(j + shift) + 8 * k]) * (cfg.predWeightChild[ii] * fracMul);
+        pred += val * (cfg.predWeightChild[ii] * fracMul);
     }
     if (present && act) {
       int64_t v = fx_mul(pred, div);
@@ -836,7 +872,8 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         if ((softM >> m) & 1) {
           const int th = thr_decode(int((codes >> (6 * m)) & 63));
           if (linked)
-            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2, hs, chunkBase, si);
+            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2, hs, chunkBase,
+                                ringSize, si);
           else
             f = tl >= th;
         }
@@ -959,65 +996,31 @@ k_block_geom(const WarpBlockArgs a)
 // (Morton = coding order) or, with a wavefront schedule, entry order[i].  Either
 // way everything a block may wait for has a lower ticket, i.e. is owned by a
 // running warp.
-// the ticket loop of one CTA (shared by the single-unit and the gang kernel)
+// the ticket loop of one CTA (shared by the single-unit and the gang kernel):
+// tickets are claimed in ascending order; ticket i runs worklist entry i
+// (Morton = coding order) or, with a wavefront schedule, entry order[i]
 __device__ __forceinline__ void
-block_ticket_loop(const WarpBlockArgs& a, unsigned long long* ticket, ChainSlot* slots,
-                  unsigned long long* sBase)
+block_ticket_loop(const WarpBlockArgs& a, unsigned long long* ticket)
 {
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
-  // coding order over a worklist: chunks of tickets, hand-over through shared memory
-  const bool chunked = a.order == nullptr && a.worklist != nullptr && a.chunked;
-  const int warp = threadIdx.x >> 5;
-  const int numWarps = blockDim.x >> 5;
-  if (chunked)
-    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
-      slots[i].tag = -1;
-      slots[i].w[0] = 0;
-      slots[i].w[1] = 0;
-    }
-  int cur = 0, end = 0, chunkBase = 0;  // chunked: this warp's next ticket, the chunk's end
-  bool inChunk = false;
   for (;;) {
-    int t;
-    if (chunked) {
-      if (cur >= end) {
-        if (inChunk)
-          __syncthreads();  // the chunk is done: its slots and *sBase may be reused
-        if (threadIdx.x == 0)
-          *sBase = atomicAdd(ticket, (unsigned long long)kChunk);
-        __syncthreads();
-        const unsigned long long base = *sBase;
-        if (base >= (unsigned long long)n)
-          return;
-        inChunk = true;
-        chunkBase = int(base);
-        end = chunkBase + kChunk < n ? chunkBase + kChunk : n;
-        cur = chunkBase + warp;
-        continue;
-      }
-      t = cur;
-      cur += numWarps;
-    } else {
-      unsigned long long base = 0;
-      if (lane == 0)
-        base = atomicAdd(ticket, 1ull);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= (unsigned long long)n)
-        return;
-      t = a.order ? a.order[base] - a.orderBase : int(base);
-    }
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 1ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)n)
+      return;
+    const int t = a.order ? a.order[base] - a.orderBase : int(base);
     const int p = a.worklist ? a.worklist[t] : 0;
-    warp_block(a, p, t, lane, chunked ? slots : nullptr, chunkBase);
+    warp_block(a, p, t, lane, nullptr, 1);
   }
 }
 
 __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
-  __shared__ ChainSlot sSlots[kChunk];
-  __shared__ unsigned long long sBase;
-  block_ticket_loop(a, ticket, sSlots, &sBase);
+  block_ticket_loop(a, ticket);
 }
 
 // A gang: several coding units (slices or frames -- independent chains with
@@ -1032,21 +1035,50 @@ struct GangEntry {
   unsigned long long* ticket;
 };
 
+__device__ __forceinline__ void
+gang_entry_to_shared(GangEntry* se, const GangEntry* src0)
+{
+  static_assert(sizeof(GangEntry) % sizeof(uint32_t) == 0, "copied by words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(src0);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(se);
+  for (int i = threadIdx.x; i < int(sizeof(GangEntry) / sizeof(uint32_t)); i += blockDim.x)
+    dst[i] = src[i];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp_gang(const GangEntry* __restrict__ tab, const int numUnits)
 {
   __shared__ GangEntry se;
-  {
-    static_assert(sizeof(GangEntry) % sizeof(uint32_t) == 0, "copied by words");
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tab + blockIdx.x % numUnits);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&se);
-    for (int i = threadIdx.x; i < int(sizeof(GangEntry) / sizeof(uint32_t)); i += blockDim.x)
-      dst[i] = src[i];
+  gang_entry_to_shared(&se, tab + blockIdx.x % numUnits);
+  block_ticket_loop(se.a, se.ticket);
+}
+
+// The chain kernel: ONE CTA per unit (entry blockIdx.x), coding order over the
+// unit's worklist, ticket t on warp t % W, hand-over through a ring of
+// 4 W slots in shared memory (see ChainSlot).  No atomics, no barriers after
+// the start.
+constexpr int kChainMaxThreads = 768;
+
+__global__ void __launch_bounds__(kChainMaxThreads, 1)
+k_block_chain_gang(const GangEntry* __restrict__ tab)
+{
+  extern __shared__ __align__(16) unsigned char dynSmem[];
+  __shared__ GangEntry se;
+  ChainSlot* slots = reinterpret_cast<ChainSlot*>(dynSmem);
+  const int numWarps = blockDim.x >> 5;
+  const int ringSize = 4 * numWarps;
+  for (int i = threadIdx.x; i < ringSize; i += blockDim.x) {
+    slots[i].tag = -1;
+    slots[i].w[0] = 0;
+    slots[i].w[1] = 0;
   }
-  __syncthreads();
-  __shared__ ChainSlot sSlots[kChunk];
-  __shared__ unsigned long long sBase;
-  block_ticket_loop(se.a, se.ticket, sSlots, &sBase);
+  gang_entry_to_shared(&se, tab + blockIdx.x);
+  const WarpBlockArgs& a = se.a;
+  const int lane = threadIdx.x & 31;
+  const int n = *a.count;
+  for (int t = threadIdx.x >> 5; t < n; t += numWarps)
+    warp_block(a, a.worklist[t], t, lane, slots, ringSize);
 }
 
 __device__ __forceinline__ int

@@ -225,9 +225,28 @@ struct WaveDescent<DeviceExec> {
       if (ec && atoi(ec) > 0 && perUnit > atoi(ec))
         perUnit = atoi(ec);
       perUnit = perUnit < 1 ? 1 : perUnit;
+      // coding order with few CTAs per unit: one CTA per unit that keeps the
+      // chain in shared memory (k_block_chain_gang); otherwise (wavefront order,
+      // the root step, a machine to fill with few units) global tickets
+      const char* ech = getenv("PCCB200_CHAIN");  // A/B: 0 = never, n = warps per chain CTA
+      const int chainWarps = ech ? atoi(ech) : 24;
+      const bool chain = d > 0 && tab[0].a.order == nullptr && chainWarps > 0 && perUnit <= 3;
       {
         DeviceExec::Scope sc(ex);
-        k_block_warp_gang<<<unsigned(perUnit * units), kWarpBlockThreads, 0, ex.stream>>>(dTab, units);
+        if (chain) {
+          int warps = chainWarps > kChainMaxThreads / 32 ? kChainMaxThreads / 32 : chainWarps;
+          warps = warps < 8 ? 8 : warps;  // (the ring must hold the look-back window)
+          const size_t smem = size_t(4 * warps) * sizeof(ChainSlot);
+          static const bool attr = [] {
+            return cudaFuncSetAttribute(k_block_chain_gang, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(4 * (kChainMaxThreads / 32) * sizeof(ChainSlot)))
+              == cudaSuccess;
+          }();
+          (void)attr;
+          k_block_chain_gang<<<unsigned(units), 32 * warps, smem, ex.stream>>>(dTab);
+        } else {
+          k_block_warp_gang<<<unsigned(perUnit * units), kWarpBlockThreads, 0, ex.stream>>>(dTab, units);
+        }
         g_launchCount++;
       }
       PCC_CUDA_CHECK(cudaGetLastError());
@@ -250,8 +269,6 @@ struct WaveDescent<DeviceExec> {
     job.rdoq = rdoq;
     const char* ep = getenv("PCCB200_POLL_NS");  // A/B knob, read per call
     const int pollNs = ep ? atoi(ep) : 32;
-    const char* ech = getenv("PCCB200_CHUNKED");  // A/B: 0 = every hand-over through L2
-    const int chunked = ech ? atoi(ech) : 1;
     static const bool mortonOrder = [] {  // A/B: coding order everywhere
       const char* e = getenv("PCCB200_WAVE_ORDER");
       return e && !strcmp(e, "morton");
@@ -315,7 +332,6 @@ struct WaveDescent<DeviceExec> {
       a.ab11a = abA;
       a.ab11b = abB;
       a.pollNs = pollNs;
-      a.chunked = chunked;
     }
     for (int d = 1; d <= top; d++) {
       const int si = top - d;

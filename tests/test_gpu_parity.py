@@ -267,22 +267,34 @@ def test_multi_batch_gang(b200, case):
         qs = qs[:1]
     p = b200.RahtParams.from_buffer_copy(bytes(params))
     q = [b200.QpSet.from_buffer_copy(bytes(x)) for x in qs]
-    for gang in ("0", "3"):  # spread over the lanes / gangs of three
+    expected = {}
+    # spread over the lanes / gangs of three with global tickets / gangs of three
+    # with one CTA per unit (hand-over through shared memory), 24 and 8 warps
+    for gang, ctas, chain in (("0", None, None), ("3", None, None), ("3", "1", None), ("4", "1", "8")):
         os.environ["PCCB200_GANG"] = gang
+        for k, v in (("PCCB200_GANG_CTAS", ctas), ("PCCB200_CHAIN", chain)):
+            os.environ.pop(k, None)
+            if v:
+                os.environ[k] = v
         recs, coefs = b200.attr_raht_encode_multi_batch(
             p, q, [x for x, _ in units], [a for _, a in units])
         for u, (xyz, attrs) in enumerate(units):
             for s, at in enumerate(attrs):
-                mort, a_s, order = sort_cloud(xyz, at)
-                orec, ocoef = oracle_raht(1, params, qs[s], mort, a_s)
-                exp = np.empty_like(orec)
-                exp[order] = np.clip(orec, 0, 255)
-                assert np.array_equal(coefs[u][s], ocoef), (case, gang, u, s)
-                assert np.array_equal(recs[u][s], exp), (case, gang, u, s)
+                if gang == "0":
+                    mort, a_s, order = sort_cloud(xyz, at)
+                    orec, ocoef = oracle_raht(1, params, qs[s], mort, a_s)
+                    exp = np.empty_like(orec)
+                    exp[order] = np.clip(orec, 0, 255)
+                    expected[(u, s)] = (ocoef, exp)
+                ocoef, exp = expected[(u, s)]
+                assert np.array_equal(coefs[u][s], ocoef), (case, gang, ctas, chain, u, s)
+                assert np.array_equal(recs[u][s], exp), (case, gang, ctas, chain, u, s)
         dec = b200.attr_raht_decode_multi_batch(p, q, [x for x, _ in units], coefs)
         for u in range(len(units)):
             for s in range(len(qs)):
-                assert np.array_equal(dec[u][s], recs[u][s]), (case, gang, u, s)
+                assert np.array_equal(dec[u][s], recs[u][s]), (case, gang, ctas, chain, u, s)
+    for k in ("PCCB200_GANG_CTAS", "PCCB200_CHAIN"):
+        os.environ.pop(k, None)
     del os.environ["PCCB200_GANG"]
 
 

@@ -80,7 +80,7 @@ def step(F):
     return pb.time_end()
 
 
-KNOBS = ("PCCB200_GANG_CTAS", "PCCB200_POLL_NS", "PCCB200_BLOCK_SHARE", "PCCB200_CHUNKED")
+KNOBS = ("PCCB200_GANG_CTAS", "PCCB200_POLL_NS", "PCCB200_BLOCK_SHARE", "PCCB200_CHAIN")
 for F, G, env in sweep:
     os.environ["PCCB200_GANG"] = str(G)
     for k in KNOBS:
