@@ -584,15 +584,17 @@ struct DeviceExec {
       numRegions = 0;
     }
     TzRegion hr;
-    hr.words = fn.tz;
-    hr.lists = fn.tz ? alloc<int>((size_t(nBlocks) + 1) * 2) : nullptr;
+    hr.state = nullptr;
+    if (fn.tz) {  // (the encoder with RDOQ: one state word per block, zero = nothing published)
+      hr.state = alloc<unsigned long long>(size_t(nBlocks) + 1);
+      zero(hr.state, (size_t(nBlocks) + 1) * sizeof(unsigned long long));
+    }
     hr.count = dCount;
     a.stageIdx = numRegions;
     upload(dRegions + numRegions, &hr, sizeof(TzRegion));
     numRegions++;
     st.regions = dRegions;
-    st.words = hr.words;
-    st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
+    st.state = hr.state;
     static const int pollNs = [] {
       const char* e = getenv("PCCB200_POLL_NS");
       return e ? atoi(e) : 32;

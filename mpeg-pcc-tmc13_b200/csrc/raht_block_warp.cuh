@@ -36,9 +36,9 @@ struct AttrSet {
   const QpTables* qt;
   int32_t* coef;         // planar coefficients, component kk at kk * coefStride
   int64_t coefStride;
-  const struct TzRegion* regions;  // zero-run words/lists of every stage so far
-  int* words;                      // regions[stageIdx].words / .lists (kernel parameters:
-  unsigned long long* lists;       //   no load on the critical path)
+  const struct TzRegion* regions;  // zero-run state words of every stage so far
+  unsigned long long* state;       // regions[stageIdx].state (kernel parameter: no load on
+                                   //   the critical path)
 };
 
 constexpr int kMaxSets = 2;
@@ -63,14 +63,40 @@ struct WarpBlockArgs {
   int orderBase;
 };
 
-// Zero-run bookkeeping of one stage, indexed by worklist rank t:
-// words[t + 1] is block t's state word, 64-bit word t + 1 of lists the
-// classification of its coefficients in scan order (6-bit codes, see below).
+// Zero-run bookkeeping of one stage, indexed by worklist rank t: state[t + 1]
+// is block t's 64-bit state word (zero = nothing published yet):
+//   bits 1:0   status (kTzTransparent / kTzExit / kTzClassified)
+//   bits 5:2   value: the block's coefficient count (transparent, classified)
+//              or the run length after the block (exit); at most 8
+//   bits 53:6  classification of its coefficients in scan order, 6 bits each
+//              (see below; present with every status once the block has soft
+//              coefficients)
+// One word, written with one relaxed 64-bit store: a consumer needs no second
+// load and the producer no release fence (the fence of a store-release waits
+// for the block's earlier stores to reach L2 -- on the critical path of the
+// chain, twice per block).
 struct TzRegion {
-  int* words;
-  int* lists;
+  unsigned long long* state;
   const int* count;
 };
+
+__device__ __forceinline__ unsigned long long
+state_pack(int status, int value, unsigned long long codes)
+{
+  return (unsigned long long)(status | (value << 2)) | codes << 6;
+}
+__device__ __forceinline__ unsigned long long
+ld_state(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void
+st_state(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 constexpr int kTzClassified = 3;  // word status: list published, outcome pending
 
@@ -201,46 +227,25 @@ rdoq_code(int64_t dist2, int64_t lambda, int rateCoeff)
 {
   const int64_t lhs = dist2 << 26;
   const int rc = (rateCoeff + 128) >> 8;
-  const int kRate[7] = {1, 2, 3, 5, 7, 9, 11};  // zero_run_rate of 0,1,2,3,5,7,9
-#pragma unroll
-  for (int i = 0; i < 7; i++)
-    if (lhs < lambda * (kRate[i] + rc))
-      return i == 0 ? kCodeRemoved : 2 + i;
-  if (lhs >= lambda * (72 + rc))  // zero_run_rate(10 + 2^29) = 72
+  // the 37 values zero_run_rate takes, ascending: 1,2,3,5,7,9,11 (tz = 0,1,2,3,5,7,9)
+  // and 12 + 2a (tz = 10 + 2^(a-1), a = 1..30); binary search for the first one
+  // that satisfies the test (the test is monotone in the rate)
+  auto rate = [](int i) { return i < 7 ? int((0xB975321u >> (4 * i)) & 15u) : 2 * i; };
+  if (lhs >= lambda * (rate(36) + rc))
     return kCodeHard;
-  for (int a = 1; a <= 30; a++)
-    if (lhs < lambda * (12 + 2 * a + rc))  // zero_run_rate(10 + 2^(a-1))
-      return 8 + a;
-  return kCodeHard;
-}
-
-// Hand-over through shared memory (the chain kernel, k_block_chain_gang).  A
-// unit whose blocks form one chain is served by ONE CTA: ticket t runs on warp
-// t % W, every warp works through its tickets in ascending order (no atomics;
-// a block waits for lower tickets only, and the lowest unfinished ticket is
-// always the current one of its warp: no deadlock).  What a block hands to the
-// blocks after it -- the reconstruction of its children, its zero-run words --
-// goes through a ring of slots (slot t % R, R = 4 W: a warp reuses its own
-// slots only) as well as through L2, and the consumer, which is on the critical
-// path of the whole stage, spins on shared memory instead of paying L2 round
-// trips.  Slots carry the full ticket number: a reader that finds an older
-// ticket waits, one that finds a later ticket (the slot has moved on) takes the
-// value from global memory, where everything is published as before; reads of
-// more than one word are validated after the fact (the owner invalidates the
-// slot before it writes anything of its next ticket).
-struct ChainSlot {
-  unsigned long long w[kMaxSets];     // (ticket + 1) << 32 | zero-run word of the set
-  unsigned long long list[kMaxSets];  // classification list (valid once the word says so)
-  int tag;                            // ticket whose rec[] is complete, -1 while it is rewritten
-  int pad;
-  long long rec[32];                  // reconstruction by lane (component row * 8 + child slot)
-};
-constexpr int kChainLookBack = 31;  // tickets behind a block that are looked for in the ring
-
-__device__ __forceinline__ unsigned long long
-slot_word(int t, int w)
-{
-  return (unsigned long long)(unsigned(t + 1)) << 32 | unsigned(w);
+  int lo = 0, hi = 36;  // invariant: the test holds at hi
+#pragma unroll
+  for (int it = 0; it < 6; it++) {
+    const int mid = (lo + hi) >> 1;
+    if (lo < hi) {
+      if (lhs < lambda * (rate(mid) + rc))
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+  }
+  // hi: index of the first rate that satisfies the test
+  return hi == 0 ? kCodeRemoved : 2 + hi;
 }
 
 // Is the run of non-resetting coefficients that ends just before block t of
@@ -261,70 +266,38 @@ slot_word(int t, int w)
 // around the poll makes every waiting warp more expensive.
 __device__ __forceinline__ bool
 tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, int need,
-                const int wPre1, const int wPre2, volatile ChainSlot* hs, const int chunkBase,
-                const int ringSize, const int si)
+                const unsigned long long wPre1, const unsigned long long wPre2)
 {
   if (need <= 0)
     return true;
   int req = need;  // positions 1..req behind the block must not reset the run
   int acc = 0;     // positions already verified
   int s = stageIdx;
-  const int* words = st.words;
-  const unsigned long long* lists = st.lists;
+  const unsigned long long* state = st.state;
   int u = t - 1;
   for (;;) {
     if (u < 0) {
       if (--s < 0)
         return acc >= req;  // start of the call: the counter starts at 0
       const TzRegion rg = st.regions[s];
-      words = rg.words;
-      lists = reinterpret_cast<const unsigned long long*>(rg.lists);
+      state = rg.state;
       u = *rg.count - 1;
       continue;
     }
-    int w = 0;
-    unsigned long long L = 0;
-    bool fromRing = false;
-    if (hs && s == stageIdx && u >= chunkBase) {
-      // a recent block of this CTA: its words are in its slot (unless the slot
-      // has moved on, which means they have long been in global memory)
-      volatile ChainSlot* h = &hs[u % ringSize];
-      for (;;) {
-        const unsigned long long v64 = h->w[si];
-        const unsigned hi = unsigned(v64 >> 32);
-        if (hi > unsigned(u + 1))
-          break;
-        if (hi == unsigned(u + 1) && tz_status(int(unsigned(v64))) != kTzNone) {
-          w = int(unsigned(v64));
-          fromRing = true;
-          if (tz_status(w) == kTzClassified) {
-            __threadfence_block();
-            L = h->list[si];
-            __threadfence_block();
-            fromRing = unsigned(h->w[si] >> 32) == unsigned(u + 1);
-          }
-          break;
-        }
-        __nanosleep(20);
-      }
+    // (words fetched ahead are as good as fresh ones unless they were empty)
+    unsigned long long w =
+      (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
+    while (tz_status(int(w)) == kTzNone) {
+      w = ld_state(&state[u + 1]);
+      if (tz_status(int(w)) != kTzNone)
+        break;
+      __nanosleep(pollNs);
     }
-    if (!fromRing) {
-      w = 0;
-      // (words fetched ahead are as good as fresh ones unless they were empty)
-      w = (s == stageIdx && u == t - 1) ? wPre1 : (s == stageIdx && u == t - 2) ? wPre2 : 0;
-      while (tz_status(w) == kTzNone) {
-        w = ld_acquire(&words[u + 1]);
-        if (tz_status(w) != kTzNone)
-          break;
-        __nanosleep(pollNs);
-      }
-      if (tz_status(w) == kTzClassified)
-        L = lists[u + 1];
-    }
-    const int st_ = tz_status(w), v = tz_value(w);
+    const int st_ = tz_status(int(w)), v = (int(w) >> 2) & 15;
     if (st_ == kTzExit)
       return v + acc >= req;
     if (st_ == kTzClassified) {
+      const unsigned long long L = w >> 6;
       for (int i = v - 1; i >= 0; i--) {
         const int pos = acc + (v - i);
         if (pos > req)
@@ -353,8 +326,7 @@ tz_run_at_least(const AttrSet& st, const int stageIdx, const int pollNs, int t, 
 // quantisers, the inherited DC), do all the arithmetic that needs only those,
 // and only then look at the values still being produced.
 __device__ __forceinline__ void
-warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
-           volatile ChainSlot* hs, const int ringSize)
+warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
 {
   const RahtConfig& cfg = a.cfg;
   const Stage& S = a.S;
@@ -377,24 +349,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
   const bool ext = cfg.ext != 0;
   const bool enc = cfg.isEncoder != 0;
   const bool rdoq = enc && !haar;
-
-  // this block's slot; the blocks of the (up to 31) tickets before it, one per
-  // lane: the likely producers of what it will wait for
-  volatile ChainSlot* me = hs ? &hs[t % ringSize] : nullptr;
-  const int chunkBase = t > kChainLookBack ? t - kChainLookBack : 0;  // oldest ticket looked for in the ring
-  int prevBlock = -1;
-  if (hs) {
-    if (lane == 0) {
-      me->tag = -1;
-      __threadfence_block();
-      me->w[0] = slot_word(t, 0);
-      me->w[1] = slot_word(t, 0);
-      __threadfence_block();
-    }
-    if (lane >= 1 && t - lane >= 0)
-      prevBlock = a.worklist[t - lane];
-    __syncwarp();
-  }
 
   const int c0 = root ? 0 : P.first[p];
   uint32_t occ;
@@ -610,20 +564,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
     // loads of up to four neighbours go out together, then whatever has not
     // been produced yet is polled
     uint32_t cm = childNb;
-    // neighbours whose block is one of the previous tickets of the chunk: bit
-    // i of localNb, the producing ticket is t - localDist (per neighbour)
-    uint32_t localNb = 0;
-    if (hs) {
-      uint32_t c2 = cm;
-      while (c2) {
-        const int i = __ffs(c2) - 1;
-        c2 &= c2 - 1;
-        const int qi = __shfl_sync(0xffffffffu, nq, i);
-        if (__ballot_sync(0xffffffffu, prevBlock == qi))
-          localNb |= 1u << i;
-      }
-      cm &= ~localNb;
-    }
     while (cm) {
       int64_t v[4];
       const int64_t* ad[4];
@@ -669,61 +609,6 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
       for (int u = 0; u < 4; u++)
         pred += v[u] * (wc[u] * fracMul);
     }
-    // the neighbours of this chunk last (they are the ones still being
-    // produced), oldest first: through shared memory
-    while (localNb) {
-      // the one produced by the lowest ticket first
-      int best = -1, bestDist = 0;
-      uint32_t c2 = localNb;
-      while (c2) {
-        const int i = __ffs(c2) - 1;
-        c2 &= c2 - 1;
-        const int qi = __shfl_sync(0xffffffffu, nq, i);
-        const int dist = __ffs(__ballot_sync(0xffffffffu, prevBlock == qi)) - 1;
-        if (dist > bestDist) {
-          bestDist = dist;
-          best = i;
-        }
-      }
-      const int i = best;
-      localNb &= ~(1u << i);
-      const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
-      const int cfirst = __shfl_sync(0xffffffffu, nfirst, i);
-      const int ii = i - 7;
-      const int sh = occu_shift(ii);
-      const int shift = ii < 9 ? sh : -sh;
-      const uint32_t cmask =
-        (ii < 9 ? (no >> sh) : (no << sh)) & uint32_t(neigh_mask(i)) & occ & 0xffu;
-      const bool need = act && ((cmask >> j) & 1) && ((validMask >> i) & 1);
-      const int r = t - bestDist;
-      volatile ChainSlot* h = &hs[r % ringSize];
-      int64_t val = 0;
-      bool got = false;
-      for (;;) {
-        if (h->tag == r) {
-          __threadfence_block();
-          val = need ? int64_t(h->rec[(j + shift) + 8 * k]) : 0;
-          __threadfence_block();
-          got = h->tag == r;  // still that block's slot: the values are its own
-          break;
-        }
-        if (unsigned(h->w[0] >> 32) > unsigned(r + 1))
-          break;  // the slot has moved on: the values are in global memory by now
-        __nanosleep(20);
-      }
-      if (!__all_sync(0xffffffffu, got)) {
-        const int c = cfirst + __popc(no & ((1u << (j + shift)) - 1));
-        const int64_t* ad1 = need ? &S.rec[size_t(c) * A + k] : nullptr;
-        val = ad1 ? ld_rec(ad1) : 0;
-        while (__any_sync(0xffffffffu, ad1 && val == kRecNotReady)) {
-          __nanosleep(a.pollNs);
-          if (ad1 && val == kRecNotReady)
-            val = ld_rec(ad1);
-        }
-      }
-      if (need)
-        pred += val * (cfg.predWeightChild[ii] * fracMul);
-    }
     if (present && act) {
       int64_t v = fx_mul(pred, div);
       if (haar)
@@ -744,12 +629,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
   // predecessor has just published its final word, and the round trip to L2
   // overlaps the arithmetic up to the block's own classification instead of
   // following it.
-  int wPre1 = 0, wPre2 = 0;
-  if (rdoq && act) {  // (inside the chunk the words come from the slots)
-    if (t >= 1 && !(hs && t - 1 >= chunkBase))
-      wPre1 = ld_acquire(&my.words[t]);
-    if (t >= 2 && !(hs && t - 2 >= chunkBase))
-      wPre2 = ld_acquire(&my.words[t - 1]);
+  unsigned long long wPre1 = 0, wPre2 = 0;
+  if (rdoq && act) {
+    if (t >= 1)
+      wPre1 = ld_state(&my.state[t]);
+    if (t >= 2)
+      wPre2 = ld_state(&my.state[t - 1]);
   }
 
   if (enc && enablePred && exists)
@@ -830,25 +715,13 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         prev = m + 1;
       }
       e += ncoef - prev;
-      if (speaker) {
-        if (me)
-          me->w[si] = slot_word(t, tz_pack(kTzExit, e));
-        st_release(&my.words[t + 1], tz_pack(kTzExit, e));
-      }
+      if (speaker)
+        st_state(&my.state[t + 1], state_pack(kTzExit, e, 0));
     } else if (!hasS) {
-      if (speaker) {
-        if (me)
-          me->w[si] = slot_word(t, tz_pack(kTzTransparent, ncoef));
-        st_release(&my.words[t + 1], tz_pack(kTzTransparent, ncoef));
-      }
+      if (speaker)
+        st_state(&my.state[t + 1], state_pack(kTzTransparent, ncoef, 0));
     } else if (speaker) {
-      if (me) {
-        me->list[si] = codes;
-        __threadfence_block();
-        me->w[si] = slot_word(t, tz_pack(kTzClassified, ncoef));
-      }
-      my.lists[t + 1] = codes;
-      st_release(&my.words[t + 1], tz_pack(kTzClassified, ncoef));
+      st_state(&my.state[t + 1], state_pack(kTzClassified, ncoef, codes));
     }
 
     // resolve this block's own decisions (each lane for its attribute): only
@@ -872,8 +745,7 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
         if ((softM >> m) & 1) {
           const int th = thr_decode(int((codes >> (6 * m)) & 63));
           if (linked)
-            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2, hs, chunkBase,
-                                ringSize, si);
+            f = tz_run_at_least(my, a.stageIdx, a.pollNs, t, th - z, wPre1, wPre2);
           else
             f = tl >= th;
         }
@@ -891,12 +763,9 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
           flagMine = f;
       }
       tl += ncoef - prev;
-      if (!hasH && speaker) {
-        const int fw = linked ? tz_pack(kTzTransparent, ncoef) : tz_pack(kTzExit, tl);
-        if (me)
-          me->w[si] = slot_word(t, fw);
-        st_release(&my.words[t + 1], fw);
-      }
+      if (!hasH && speaker)
+        st_state(&my.state[t + 1], linked ? state_pack(kTzTransparent, ncoef, 0)
+                                          : state_pack(kTzExit, tl, 0));
     }
   }
 
@@ -919,24 +788,12 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane,
 #pragma unroll
   for (int s = 2; s >= 0; s--)
     pred = bfly_inv(pred, bf[s], 1 << s, haar);
-  int64_t recOut = 0;
   if (present && act) {
     int64_t v = pred;
+    S.recUs[size_t(cidx) * A + k] = ext ? v : fx_round(v * 4);
     if (rsMul)
       v = fx_mul(v >> rsShift, rsMul);
-    recOut = ext ? v : fx_round(v);
-  }
-  if (me) {  // first where the next block of the chain looks first
-    me->rec[lane] = recOut;
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      me->tag = t;
-    }
-  }
-  if (present && act) {
-    st_rec(&S.rec[size_t(cidx) * A + k], recOut);
-    S.recUs[size_t(cidx) * A + k] = ext ? pred : fx_round(pred * 4);
+    st_rec(&S.rec[size_t(cidx) * A + k], ext ? v : fx_round(v));
   }
 }
 
@@ -996,11 +853,8 @@ k_block_geom(const WarpBlockArgs a)
 // (Morton = coding order) or, with a wavefront schedule, entry order[i].  Either
 // way everything a block may wait for has a lower ticket, i.e. is owned by a
 // running warp.
-// the ticket loop of one CTA (shared by the single-unit and the gang kernel):
-// tickets are claimed in ascending order; ticket i runs worklist entry i
-// (Morton = coding order) or, with a wavefront schedule, entry order[i]
-__device__ __forceinline__ void
-block_ticket_loop(const WarpBlockArgs& a, unsigned long long* ticket)
+__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
+k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
 {
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
@@ -1013,14 +867,8 @@ block_ticket_loop(const WarpBlockArgs& a, unsigned long long* ticket)
       return;
     const int t = a.order ? a.order[base] - a.orderBase : int(base);
     const int p = a.worklist ? a.worklist[t] : 0;
-    warp_block(a, p, t, lane, nullptr, 1);
+    warp_block(a, p, t, lane);
   }
-}
-
-__global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
-k_block_warp(const WarpBlockArgs a, unsigned long long* ticket)
-{
-  block_ticket_loop(a, ticket);
 }
 
 // A gang: several coding units (slices or frames -- independent chains with
@@ -1035,50 +883,33 @@ struct GangEntry {
   unsigned long long* ticket;
 };
 
-__device__ __forceinline__ void
-gang_entry_to_shared(GangEntry* se, const GangEntry* src0)
-{
-  static_assert(sizeof(GangEntry) % sizeof(uint32_t) == 0, "copied by words");
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(src0);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(se);
-  for (int i = threadIdx.x; i < int(sizeof(GangEntry) / sizeof(uint32_t)); i += blockDim.x)
-    dst[i] = src[i];
-  __syncthreads();
-}
-
 __global__ void __launch_bounds__(kWarpBlockThreads, PCCB200_BLOCK_MIN_CTAS)
 k_block_warp_gang(const GangEntry* __restrict__ tab, const int numUnits)
 {
   __shared__ GangEntry se;
-  gang_entry_to_shared(&se, tab + blockIdx.x % numUnits);
-  block_ticket_loop(se.a, se.ticket);
-}
-
-// The chain kernel: ONE CTA per unit (entry blockIdx.x), coding order over the
-// unit's worklist, ticket t on warp t % W, hand-over through a ring of
-// 4 W slots in shared memory (see ChainSlot).  No atomics, no barriers after
-// the start.
-constexpr int kChainMaxThreads = 768;
-
-__global__ void __launch_bounds__(kChainMaxThreads, 1)
-k_block_chain_gang(const GangEntry* __restrict__ tab)
-{
-  extern __shared__ __align__(16) unsigned char dynSmem[];
-  __shared__ GangEntry se;
-  ChainSlot* slots = reinterpret_cast<ChainSlot*>(dynSmem);
-  const int numWarps = blockDim.x >> 5;
-  const int ringSize = 4 * numWarps;
-  for (int i = threadIdx.x; i < ringSize; i += blockDim.x) {
-    slots[i].tag = -1;
-    slots[i].w[0] = 0;
-    slots[i].w[1] = 0;
+  {
+    static_assert(sizeof(GangEntry) % sizeof(uint32_t) == 0, "copied by words");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tab + blockIdx.x % numUnits);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&se);
+    for (int i = threadIdx.x; i < int(sizeof(GangEntry) / sizeof(uint32_t)); i += blockDim.x)
+      dst[i] = src[i];
   }
-  gang_entry_to_shared(&se, tab + blockIdx.x);
+  __syncthreads();
   const WarpBlockArgs& a = se.a;
+  unsigned long long* const ticket = se.ticket;
   const int lane = threadIdx.x & 31;
   const int n = *a.count;
-  for (int t = threadIdx.x >> 5; t < n; t += numWarps)
-    warp_block(a, a.worklist[t], t, lane, slots, ringSize);
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 1ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)n)
+      return;
+    const int t = a.order ? a.order[base] - a.orderBase : int(base);
+    const int p = a.worklist ? a.worklist[t] : 0;
+    warp_block(a, p, t, lane);
+  }
 }
 
 __device__ __forceinline__ int

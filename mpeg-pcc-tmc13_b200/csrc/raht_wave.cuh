@@ -42,7 +42,8 @@ struct LevelArgs {
   int rowOff[kMaxWaveSegs + 2]; // rowOff[d]; rowOff[numSeg + 1] = number of rows
   const int* cnt;               // cnt[d]: transforming blocks of segment d
   const int32_t* wl;            // row -> block index (first cnt[d] rows of a segment)
-  const int32_t* geom;          // kGeomStride ints per row
+  const int32_t* geom;          // kGeomStride ints per transforming block, segment d at geomOff[d]
+  int geomOff[kMaxWaveSegs + 2];
   int* lv;                      // per (segment, block index): dependency level, 0 = not known yet
   int64_t* key;                 // per row: segment << 16 | level (0xffff: unused row)
   int32_t* val;                 // per row: the row itself
@@ -96,7 +97,7 @@ k_block_levels(const LevelArgs a, unsigned long long* ticket)
       q[i] = 0;
     if (active) {
       p = a.wl[row];
-      const int32_t* g = a.geom + size_t(row) * kGeomStride;
+      const int32_t* g = a.geom + (size_t(a.geomOff[d]) + t) * kGeomStride;
       depMask = (uint32_t(g[19]) >> 8) & 0xfffu;
 #pragma unroll
       for (int i = 0; i < 12; i++)
@@ -166,6 +167,7 @@ struct WaveDescent<DeviceExec> {
     bool rdoq = false;
     std::vector<WarpBlockArgs> args;   // one per descent step, [0] = root block
     int rowOff[kMaxWaveSegs + 2] = {};
+    int blocks[kMaxWaveSegs + 2] = {};  // transforming blocks of every step
     const int32_t* order = nullptr;
     int* cntRoot = nullptr;
     unsigned long long* tickets = nullptr;
@@ -225,28 +227,9 @@ struct WaveDescent<DeviceExec> {
       if (ec && atoi(ec) > 0 && perUnit > atoi(ec))
         perUnit = atoi(ec);
       perUnit = perUnit < 1 ? 1 : perUnit;
-      // coding order with few CTAs per unit: one CTA per unit that keeps the
-      // chain in shared memory (k_block_chain_gang); otherwise (wavefront order,
-      // the root step, a machine to fill with few units) global tickets
-      const char* ech = getenv("PCCB200_CHAIN");  // A/B: 0 = never, n = warps per chain CTA
-      const int chainWarps = ech ? atoi(ech) : 24;
-      const bool chain = d > 0 && tab[0].a.order == nullptr && chainWarps > 0 && perUnit <= 3;
       {
         DeviceExec::Scope sc(ex);
-        if (chain) {
-          int warps = chainWarps > kChainMaxThreads / 32 ? kChainMaxThreads / 32 : chainWarps;
-          warps = warps < 8 ? 8 : warps;  // (the ring must hold the look-back window)
-          const size_t smem = size_t(4 * warps) * sizeof(ChainSlot);
-          static const bool attr = [] {
-            return cudaFuncSetAttribute(k_block_chain_gang, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(4 * (kChainMaxThreads / 32) * sizeof(ChainSlot)))
-              == cudaSuccess;
-          }();
-          (void)attr;
-          k_block_chain_gang<<<unsigned(units), 32 * warps, smem, ex.stream>>>(dTab);
-        } else {
-          k_block_warp_gang<<<unsigned(perUnit * units), kWarpBlockThreads, 0, ex.stream>>>(dTab, units);
-        }
+        k_block_warp_gang<<<unsigned(perUnit * units), kWarpBlockThreads, 0, ex.stream>>>(dTab, units);
         g_launchCount++;
       }
       PCC_CUDA_CHECK(cudaGetLastError());
@@ -289,7 +272,6 @@ struct WaveDescent<DeviceExec> {
       job.rowOff[d] = la.rowOff[d];
 
     int32_t* wl = ex.alloc<int32_t>(size_t(numRows));
-    int32_t* geom = cfg.predictionEnabled ? ex.alloc<int32_t>(size_t(numRows) * kGeomStride) : nullptr;
     int* cnt = ex.alloc<int>(top + 2);  // [0]: root step, [d]: step d
     // zeroed in one go: the ticket word of every step, the levels
     const size_t zInts = size_t(top + 2) * 2 + (wave ? size_t(numRows) : 0);
@@ -299,8 +281,40 @@ struct WaveDescent<DeviceExec> {
     int* lv = zero + size_t(top + 2) * 2;
     job.tickets = tickets;
 
-    //-- 1. geometry, top-down
+    //-- 0. worklists of all steps (they follow from the tree alone); their sizes
+    //   go to the host (one read-back) so that the neighbour tables -- 80 bytes
+    //   per transforming block, the largest item of a unit's workspace -- are
+    //   allocated for the blocks that transform (a third of all blocks on the
+    //   bench frame), not for every block
     ex.phase(kPhaseGeom);
+    int* cntRoot = cnt;  // cnt[0]: the root step has one block
+    job.cntRoot = cntRoot;
+    {
+      int one = 1;
+      ex.upload(cntRoot, &one, sizeof(int));
+    }
+    for (int d = 1; d <= top; d++)
+      ex.compact(stages[top - d + 1].n, MultiChildPred{stages[top - d + 1].first},
+                 WorklistEmit{wl + la.rowOff[d]}, cnt + d);
+    int hostCnt[kMaxWaveSegs + 2] = {};
+    int32_t* geom = nullptr;
+    la.geomOff[0] = 0;
+    if (top >= 1)
+      ex.download(hostCnt, cnt, size_t(top + 1) * sizeof(int));
+    hostCnt[0] = 1;
+    for (int d = 0; d <= top; d++)
+      job.blocks[d] = hostCnt[d];
+    if (cfg.predictionEnabled) {
+      int64_t total = 0;
+      for (int d = 1; d <= top; d++) {
+        la.geomOff[d] = int(total);
+        total += hostCnt[d];
+      }
+      la.geomOff[top + 1] = int(total);
+      geom = ex.alloc<int32_t>(size_t(total) * kGeomStride);
+    }
+
+    //-- 1. geometry, top-down
     ex.foreach(stages[top].n, FillI32{stages[top].nn, 19});
     if (cfg.hasQp)
       ex.foreach(1, RootQpFn{stages[top]});
@@ -308,12 +322,6 @@ struct WaveDescent<DeviceExec> {
     raht_ab(1, 1, abA, abB);
     std::vector<WarpBlockArgs>& args = job.args;
     args.assign(top + 1, WarpBlockArgs{});
-    int* cntRoot = cnt;  // cnt[0]: the root step has one block
-    job.cntRoot = cntRoot;
-    {
-      int one = 1;
-      ex.upload(cntRoot, &one, sizeof(int));
-    }
     for (int d = 0; d <= top; d++) {
       WarpBlockArgs& a = args[d];
       a.cfg = cfg;
@@ -341,18 +349,17 @@ struct WaveDescent<DeviceExec> {
       PrepFn prep{cfg, S, P, cfg.predictionEnabled, nullptr, 1};
       if (cfg.hasQp || cfg.predictionEnabled)
         ex.foreach(nBlocks, prep);
-      ex.compact(nBlocks, MultiChildPred{P.first}, WorklistEmit{wl + la.rowOff[d]}, cnt + d);
       WarpBlockArgs& a = args[d];
       a.S = S;
       a.P = P;
       a.coefBase = P.n;
       a.predInLvl = cfg.predictionEnabled;
       a.worklist = wl + la.rowOff[d];
-      a.geom = geom ? geom + size_t(la.rowOff[d]) * kGeomStride : nullptr;
+      a.geom = geom ? geom + size_t(la.geomOff[d]) * kGeomStride : nullptr;
       a.count = cnt + d;
-      if (cfg.predictionEnabled) {
+      if (cfg.predictionEnabled && hostCnt[d] > 0) {
         DeviceExec::Scope sc(ex);
-        k_block_geom<<<unsigned((int64_t(nBlocks) * 32 + 255) / 256), 256, 0, ex.stream>>>(a);
+        k_block_geom<<<unsigned((int64_t(hostCnt[d]) * 32 + 255) / 256), 256, 0, ex.stream>>>(a);
         g_launchCount++;
       }
     }
@@ -385,15 +392,37 @@ struct WaveDescent<DeviceExec> {
       job.order = vres;
     }
 
-    if (rdoq)
-      for (int s = 0; s < numSets; s++)
+    // zero-run state words: one region of (blocks + 1) words per descent step
+    // and attribute, all zeroed ("nothing published") in one go; the table of
+    // regions (for the walk across steps) is uploaded once
+    if (rdoq) {
+      int64_t stateOff[kMaxWaveSegs + 3];
+      stateOff[0] = 0;
+      stateOff[1] = 2;
+      for (int d = 1; d <= top; d++)
+        stateOff[d + 1] = stateOff[d] + stages[top - d + 1].n + 1;
+      const size_t words = size_t(stateOff[top + 1]);
+      unsigned long long* state = ex.alloc<unsigned long long>(words * numSets);
+      ex.zero(state, words * numSets * sizeof(unsigned long long));
+      for (int s = 0; s < numSets; s++) {
+        TzRegion hr[kMaxWaveSegs + 2];
+        for (int d = 0; d <= top; d++) {
+          hr[d].state = state + words * s + stateOff[d];
+          hr[d].count = d == 0 ? cntRoot : cnt + d;
+          args[d].set[s].state = hr[d].state;
+        }
         job.dRegions[s] = ex.alloc<TzRegion>(kMaxWaveSegs + 2);
+        ex.upload(job.dRegions[s], hr, sizeof(TzRegion) * (top + 1));
+        for (int d = 0; d <= top; d++)
+          args[d].set[s].regions = job.dRegions[s];
+      }
+    }
     PCC_CUDA_CHECK(cudaGetLastError());
   }
 
   //-- 4. what precedes the block kernel of descent step d: reconstruction
   //   slots armed, single-child blocks passed through (they read the previous
-  //   step's results), the step's zero-run region.  Returns its block count.
+  //   step's results).  Returns the number of blocks the kernel will run.
   static int stage_prep(DeviceExec& ex, Job& job, int d)
   {
     const RahtConfig& cfg = job.cfg;
@@ -424,18 +453,8 @@ struct WaveDescent<DeviceExec> {
       AttrSet& st = a.set[s];
       st.qpLayer = d + 1 < job.rt[s].numLayers ? d + 1 : job.rt[s].numLayers - 1;
       st.acLayer = d;
-      if (job.rdoq) {
-        TzRegion hr;
-        hr.words = job.rt[s].tz + job.tzOff[si];
-        hr.lists = ex.alloc<int>((size_t(nBlocks) + 1) * 2);
-        hr.count = a.count;
-        ex.upload(job.dRegions[s] + d, &hr, sizeof(TzRegion));
-        st.regions = job.dRegions[s];
-        st.words = hr.words;
-        st.lists = reinterpret_cast<unsigned long long*>(hr.lists);
-      }
     }
-    return nBlocks;
+    return job.blocks[d];
   }
 };
 
