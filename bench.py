@@ -10,7 +10,7 @@ lossy-attrs CTC settings (qp 34, chroma offset -2, prediction + sub-node
 prediction on, search range 2500).  One step = the attribute coder's RAHT hot
 path over one frame: for colour (A=3) and for reflectance (A=1), Morton key +
 sort, gather, forward transform (RDOQ + quantisation + reconstruction), clip
-and write back.  A step processes --frames (default 128) independent frames of
+and write back.  A step processes --frames (default 160) independent frames of
 that shape per GPU in ONE batch call (pccb200_attr_raht_encode_multi_batch: the
 library codes them in gangs, many dependency chains in flight; intra-coded frames,
 slices and attributes are independent work units in the reference,
@@ -64,7 +64,7 @@ METRIC = "attribute-transform Mpoints/s (RAHT forward: Morton sort + transform, 
 ALG_BYTES_PER_POINT = (16 + 12 * 3) + (16 + 12 * 1)  # 52 (RGB) + 28 (reflectance)
 
 
-FRAMES_PER_STEP = 128  # frames in flight per GPU: one batch call, coded in gangs
+FRAMES_PER_STEP = 160  # frames in flight per GPU: one batch call, coded in gangs
 DISTINCT_FRAMES = 16   # distinct synthetic frames (geometry + attributes) the step cycles through
 
 

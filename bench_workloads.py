@@ -131,14 +131,22 @@ def run(args, bench):
         crgb = [torch.empty((3, int(offs[s + 1] - offs[s])), dtype=torch.int32, device=dev) for s in range(ns)]
         crefl = [torch.empty((1, int(offs[s + 1] - offs[s])), dtype=torch.int32, device=dev) for s in range(ns)]
 
-        def slice_job(s):
+        def slice_job(s):  # (one slice alone: the per-phase profile leg)
             o, n = int(offs[s]), int(offs[s + 1] - offs[s])
             pb.attr_raht_encode_multi_dev(
                 params, [qpset, qpset], dxyz.data_ptr() + 12 * o,
                 [drgb.data_ptr() + 12 * o, drefl.data_ptr() + 4 * o],
                 [crgb[s].data_ptr(), crefl[s].data_ptr()], n, [3, 1])
 
-        jobs = [lambda s=s: slice_job(s) for s in range(ns)]
+        def all_slices():  # the slices of the frame in ONE batch call (coded in gangs)
+            pb.attr_raht_multi_batch_dev(
+                True, params, [qpset, qpset], [dxyz.data_ptr() + 12 * int(offs[s]) for s in range(ns)],
+                [[drgb.data_ptr() + 12 * int(offs[s]), drefl.data_ptr() + 4 * int(offs[s])] for s in range(ns)],
+                [[crgb[s].data_ptr(), crefl[s].data_ptr()] for s in range(ns)],
+                [int(offs[s + 1] - offs[s]) for s in range(ns)], [3, 1])
+
+        jobs = [all_slices]
+        one_slice = lambda: slice_job(0)
         resident = "device-resident inputs and outputs"
 
     def prepare():
@@ -185,6 +193,8 @@ def run(args, bench):
             C.byref(lp), C.byref(lq), C.c_int32(1), None, pb._p(xyz, C.c_int32), pb._p(o1, C.c_int32),
             C.c_int32(3), C.c_int32(8), pb._p(so1, C.c_int64), C.c_int32(1), pb._p(v1, C.c_int32),
             pb._p(l1, C.c_int8)))
+    elif name == "raht30m":
+        one_slice()
     else:
         jobs[0]()
     pb.profile_enable(False)

@@ -606,6 +606,9 @@ attr_raht_multi_common(bool forward, bool device, const pccb200_raht_params* par
 // flight is what the device's throughput follows, and with gangs it is no
 // longer limited by the number of hardware queues.
 constexpr int kMaxGang = 32;
+constexpr int kBatchLanes = 16;  // lanes a batch call spreads over (measured: 8, 16 and 32 lanes
+                                 // give the same throughput; fewer lanes = fewer host threads
+                                 // and fewer launches)
 
 int
 attr_raht_batch_common(bool forward, bool device, const pccb200_raht_params* params, int numSets,
@@ -643,7 +646,7 @@ attr_raht_batch_common(bool forward, bool device, const pccb200_raht_params* par
   // (PCCB200_GANG: A/B knob, read per call)
   const char* eg = getenv("PCCB200_GANG");
   const int envGang = eg ? atoi(eg) : 0;
-  int gang = envGang > 0 ? envGang : (numUnits + kMaxLanes - 1) / kMaxLanes;
+  int gang = envGang > 0 ? envGang : (numUnits + kBatchLanes - 1) / kBatchLanes;
   gang = gang > kMaxGang ? kMaxGang : gang;
   const int numGangs = (numUnits + gang - 1) / gang;
   return parallel_for(numGangs, kMaxLanes, [&](int g) -> int {

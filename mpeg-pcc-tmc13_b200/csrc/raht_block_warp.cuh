@@ -364,7 +364,10 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
   //-- prediction gating: neighbour indices and count come from k_block_geom;
   //   lane i < 19 fetches what the prediction needs of neighbour i
   bool enablePred = false;
-  int64_t nv0 = 0, nv1 = 0, nv2 = 0, nv3 = 0;  // its reconstruction at the parent stage
+  // reconstruction of the neighbours at the parent stage: lane (k, m) holds
+  // component k of neighbours m, m + 8 and m + 16, so that a lane gets the
+  // component it needs of neighbour i with one exchange (from lane (k, i & 7))
+  int64_t nvr0 = 0, nvr1 = 0, nvr2 = 0;
   uint32_t nocc = 0;                  // its occupancy, if its children may be used
   int nfirst = 0;                     // and its first child
   uint32_t validMask = 0;             // neighbours that contribute (to this lane's attribute)
@@ -377,32 +380,40 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
     enablePred = count >= cfg.thr1 && __shfl_sync(0xffffffffu, g, 0) >= 0;
     if (enablePred) {
       const int parentOnly = cfg.subnode ? 7 : 19;
-      if (nq >= 0) {
-        nv0 = P.rec[size_t(nq) * A];
-        if (A > 1)
-          nv1 = P.rec[size_t(nq) * A + 1];
-        if (A > 2)
-          nv2 = P.rec[size_t(nq) * A + 2];
-        if (A > 3)
-          nv3 = P.rec[size_t(nq) * A + 3];
-        if (lane >= parentOnly && nq < p) {
-          nocc = P.occ[nq];
-          nfirst = P.first[nq];
-        }
+      const int q0 = __shfl_sync(0xffffffffu, nq, j);
+      const int q1 = __shfl_sync(0xffffffffu, nq, j + 8);
+      const int q2 = __shfl_sync(0xffffffffu, nq, j + 16);  // (lanes 19..23 hold -1)
+      if (act) {
+        if (q0 >= 0)
+          nvr0 = P.rec[size_t(q0) * A + k];
+        if (q1 >= 0)
+          nvr1 = P.rec[size_t(q1) * A + k];
+        if (q2 >= 0)
+          nvr2 = P.rec[size_t(q2) * A + k];
+      }
+      if (lane >= parentOnly && nq >= 0 && nq < p) {
+        nocc = P.occ[nq];
+        nfirst = P.first[nq];
       }
       // neighbours whose first component is out of range of the block's own
-      // parent are ignored (RAHT.cpp:392-404): one test per attribute
-      const int64_t self = shfl_i64(nv0, 0);
+      // parent are ignored (RAHT.cpp:392-404): one test per attribute, on the
+      // row of its first component
+      const int64_t self = shfl_i64(nvr0, lane & 24);
       const int64_t limLow = 2 * self, limHigh = 25 * self;
-      const bool ok = nq >= 0 && (lane == 0 || (10 * nv0 > limLow && 10 * nv0 < limHigh));
-      validMask = __ballot_sync(0xffffffffu, ok);
+      const bool ok0 = q0 >= 0 && (j == 0 || (10 * nvr0 > limLow && 10 * nvr0 < limHigh));
+      const bool ok1 = q1 >= 0 && 10 * nvr1 > limLow && 10 * nvr1 < limHigh;
+      const bool ok2 = q2 >= 0 && 10 * nvr2 > limLow && 10 * nvr2 < limHigh;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, ok0);
+      const uint32_t b1 = __ballot_sync(0xffffffffu, ok1);
+      const uint32_t b2 = __ballot_sync(0xffffffffu, ok2);
+      auto row_mask = [&](int row) {
+        const int sh = 8 * row;
+        return ((b0 >> sh) & 0xffu) | ((b1 >> sh) & 0xffu) << 8 | ((b2 >> sh) & 0x7u) << 16;
+      };
+      validMask = row_mask(0);
       validAny = validMask;
       if (a.numSets > 1) {
-        const int64_t f1 = base1 == 1 ? nv1 : base1 == 2 ? nv2 : nv3;
-        const int64_t self1 = shfl_i64(f1, 0);
-        const bool ok1 =
-          nq >= 0 && (lane == 0 || (10 * f1 > 2 * self1 && 10 * f1 < 25 * self1));
-        const uint32_t valid1 = __ballot_sync(0xffffffffu, ok1);
+        const uint32_t valid1 = row_mask(base1);
         validAny |= valid1;
         if (si)
           validMask = valid1;
@@ -524,16 +535,8 @@ warp_block(const WarpBlockArgs& a, const int p, const int t, const int lane)
       vm &= vm - 1;
       const bool counts = (validMask >> i) & 1;  // for this lane's attribute
       const uint32_t no = __shfl_sync(0xffffffffu, nocc, i);
-      int64_t mine = shfl_i64(nv0, i);
-      if (A > 1) {
-        const int64_t m1 = shfl_i64(nv1, i);
-        const int64_t m2 = shfl_i64(nv2, i);
-        mine = k == 0 ? mine : k == 1 ? m1 : m2;
-      }
-      if (A > 3) {
-        const int64_t m3 = shfl_i64(nv3, i);
-        mine = k == 3 ? m3 : mine;
-      }
+      const int64_t src = i < 8 ? nvr0 : i < 16 ? nvr1 : nvr2;
+      const int64_t mine = shfl_i64(src, (lane & 24) | (i & 7));
       const uint32_t mask = uint32_t(neigh_mask(i)) & occ;
       uint32_t cmask = 0;
       if (no) {  // only fetched for i >= parentOnly && q < p
