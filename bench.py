@@ -553,10 +553,11 @@ def run_ours(args):
     hv = []
     for u in range(F):
         x, r, l = hsrc[u % D]
-        hv.append({"xyz": x, "rgb0": r, "refl0": l, "rgb": torch.empty_like(r).pin_memory(),
-                   "refl": torch.empty_like(l).pin_memory(),
-                   "crgb": torch.empty((3, n), dtype=torch.int32).pin_memory(),
-                   "crefl": torch.empty((1, n), dtype=torch.int32).pin_memory()})
+        hv.append({"xyz": x, "rgb0": r, "refl0": l,
+                   "rgb": torch.empty(r.shape, dtype=r.dtype, pin_memory=True),
+                   "refl": torch.empty(l.shape, dtype=l.dtype, pin_memory=True),
+                   "crgb": torch.empty((3, n), dtype=torch.int32, pin_memory=True),
+                   "crefl": torch.empty((1, n), dtype=torch.int32, pin_memory=True)})
 
     def host_jobs():
         return [lambda: pb.attr_raht_encode_multi_batch_into(
