@@ -59,3 +59,40 @@ def test_no_cpu_fallback():
     with pytest.raises(pb.PccB200Error):
         pb.raht_forward(pb.default_params(), q, np.arange(4, dtype=np.int64),
                         np.zeros((4, 3), dtype=np.int32))
+
+
+def test_batch_entry_argument_checks():
+    """The many-units entry validates its arguments before it looks for a
+    device: nulls, empty units and more than four components are refused with
+    PCCB200_ERR_INVALID_ARG; a well-formed call without a GPU fails loudly."""
+    import torch
+
+    import pcc_attr_b200 as pb
+    from pcc_testlib import make_qpset
+
+    q = pb.QpSet.from_buffer_copy(bytes(make_qpset()))
+    p = pb.default_params()
+    xyz = [np.zeros((8, 3), dtype=np.int32), np.zeros((5, 3), dtype=np.int32)]
+    rgb = [np.zeros((8, 3), dtype=np.int32), np.zeros((5, 3), dtype=np.int32)]
+    lib = pb.lib()
+    k, m = 1, 2
+    QP = C.POINTER(pb.QpSet) * k
+    VP = C.c_void_p * m
+    coefs = [np.zeros((3, 8), dtype=np.int32), np.zeros((3, 5), dtype=np.int32)]
+
+    def call(xp, ap, cp, na, ns):
+        return lib.pccb200_attr_raht_encode_multi_batch(
+            C.byref(p), C.c_int32(k), QP(C.pointer(q)), C.c_int32(m), xp, ap,
+            (C.c_int32 * k)(*na), (C.c_int32 * k)(8), (C.c_int32 * m)(*ns), cp)
+
+    good = (VP(*[x.ctypes.data for x in xyz]), VP(*[a.ctypes.data for a in rgb]),
+            VP(*[c.ctypes.data for c in coefs]))
+    invalid = 1  # PCCB200_ERR_INVALID_ARG
+    assert call(None, good[1], good[2], [3], [8, 5]) == invalid
+    assert call(VP(xyz[0].ctypes.data, None), good[1], good[2], [3], [8, 5]) == invalid
+    assert call(good[0], good[1], good[2], [3], [8, 0]) == invalid
+    assert call(good[0], good[1], good[2], [5], [8, 5]) == invalid
+    if not torch.cuda.is_available():
+        rc = call(good[0], good[1], good[2], [3], [8, 5])
+        assert rc != 0 and rc != invalid
+        assert b"CUDA" in lib.pccb200_last_error() or b"device" in lib.pccb200_last_error()
