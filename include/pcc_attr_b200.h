@@ -458,7 +458,11 @@ int pccb200_attr_lift_decode_slices(const pccb200_lod_params* lod, const pccb200
  * call of the slice then run the lifting passes only. */
 typedef struct pccb200_lod_handle_s* pccb200_lod_handle;
 
-/* Builds the levels of detail of xyz (N x 3, host) on the selected device. */
+/* Builds the levels of detail of xyz (N x 3, host) on the selected device:
+ * predictors and coding order.  The lifting quantisation weights are computed
+ * by the first pccb200_attr_lift_*_lod call on the handle (a handle made for the
+ * predicting transform, whose predictors reference their own level of detail,
+ * never needs them). */
 int pccb200_lod_create(const pccb200_lod_params* params, const int32_t* xyz, int32_t n,
                        pccb200_lod_handle* handle_out);
 void pccb200_lod_destroy(pccb200_lod_handle handle);

@@ -30,7 +30,8 @@ struct LodState {
 // fills st (preds / idx / qw must point to n entries each)
 template<class Exec>
 int
-lod_state_build(Exec& ex, const pccb200_lod_params& lod, const int32_t* xyz, int n, LodState& st)
+lod_state_build(Exec& ex, const pccb200_lod_params& lod, const int32_t* xyz, int n, LodState& st,
+                bool withWeights = true)
 {
   st.n = n;
   st.numDetailLevels = lod.num_detail_levels;
@@ -38,6 +39,11 @@ lod_state_build(Exec& ex, const pccb200_lod_params& lod, const int32_t* xyz, int
   int rc = lod_run(ex, lod, xyz, n, st.preds, st.idx, st.npl, &st.lodCount);
   if (rc != PCCB200_OK)
     return rc;
+  // (the quantisation weights belong to the lifting transform; a caller that
+  // may only need the predictors -- the predicting transform, whose coding loop
+  // stays on the host -- asks for them later)
+  if (!withWeights)
+    return PCCB200_OK;
   return run_quant_weights(ex, st.preds, n, st.npl, st.lodCount, st.qw);
 }
 

@@ -1205,6 +1205,10 @@ struct pccb200_lod_handle_s {
   pccb200_lod_params params;
   pccb200::LodState st;
   void* block;  // one device allocation behind preds / idx / qw
+  // the lifting quantisation weights are computed by the first lifting call on
+  // the handle (a handle made for the predicting transform never needs them)
+  std::mutex qwMu;
+  bool qwReady = false;
 };
 
 namespace {
@@ -1233,6 +1237,16 @@ attr_lift_lod_common(bool forward, pccb200_lod_handle h, const pccb200_qpset* qp
     int32_t* dV = forward ? ex.alloc<int32_t>(size_t(n) * A)
                           : pccb200::to_device(ex, values, size_t(n) * A);
     int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+    {
+      std::lock_guard<std::mutex> g(h->qwMu);
+      if (!h->qwReady) {
+        int rcq = pccb200::run_quant_weights(ex, h->st.preds, n, h->st.npl, h->st.lodCount, h->st.qw);
+        if (rcq != PCCB200_OK)
+          return pccb200::fail(rcq, "invalid levels of detail");
+        PCC_CUDA_CHECK(cudaStreamSynchronize(ex.stream));  // other lanes read them from now on
+        h->qwReady = true;
+      }
+    }
     int rc2 = pccb200::attr_lift_on_lods(ex, forward, h->st, *qpset, lcpEnabled != 0, dQpoIn, dIn,
                                          dOut, A, bitdepth, dV, lcpLocal);
     if (rc2 != PCCB200_OK)
@@ -1277,7 +1291,7 @@ pccb200_lod_create(const pccb200_lod_params* params, const int32_t* xyz, int32_t
     h->st.qw = reinterpret_cast<uint64_t*>(b + szP);
     h->st.idx = reinterpret_cast<uint32_t*>(b + szP + szQ);
     int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
-    int rc2 = lod_state_build(ex, *params, dXyz, n, h->st);
+    int rc2 = lod_state_build(ex, *params, dXyz, n, h->st, false);
     if (rc2 != PCCB200_OK)
       return fail(rc2, "invalid LoD parameters");
     return PCCB200_OK;

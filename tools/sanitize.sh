@@ -1,9 +1,10 @@
 #!/bin/bash
 # developer tool (run under gpurun): compute-sanitizer over small RAHT encodes /
 # decodes (single attribute, two attributes in one pass) and a lifting encode
-# with distance subsampling (k_subsample_cells).  racecheck looks at shared
-# memory only: it is run with PCCB200_HANDOVER=0 (the shared-memory hand-over of
-# k_block_warp is a flag protocol between warps without a barrier, by design).
+# decodes (single attribute, two attributes in one pass, a gang of units in one
+# batch call) and a lifting encode with distance subsampling (k_subsample_cells).
+# racecheck looks at shared memory only (the block kernels hand values over
+# through global memory with relaxed / acquire-release accesses).
 cat > /tmp/san.py <<'PY'
 import os, sys
 ROOT = os.environ.get("GRAFT_REPO_ROOT", "/root/repo")
@@ -25,6 +26,15 @@ recs, coefs = pb.attr_raht_encode_multi(p, [q, q], xyz, [attrs, refl])
 assert np.array_equal(coefs[0], ocoef)
 decs = pb.attr_raht_decode_multi(p, [q, q], xyz, coefs)
 assert np.array_equal(decs[0], recs[0]) and np.array_equal(decs[1], recs[1])
+units = [cloud_shell(3000 + 700 * u, bits=6 + u % 2, seed=20 + u) for u in range(5)]
+uat = [[texture(a, 20, 30 + u), texture(a[:, :1].copy(), 12, 40 + u)] for u, (x, a) in enumerate(units)]
+os.environ["PCCB200_GANG"] = "3"
+brec, bcoef = pb.attr_raht_encode_multi_batch(p, [q, q], [x for x, _ in units], uat)
+for u, (x, _) in enumerate(units):
+    r1, c1 = pb.attr_raht_encode_multi(p, [q, q], x, uat[u])
+    assert all(np.array_equal(bcoef[u][s], c1[s]) and np.array_equal(brec[u][s], r1[s]) for s in range(2))
+bdec = pb.attr_raht_decode_multi_batch(p, [q, q], [x for x, _ in units], bcoef)
+assert all(np.array_equal(bdec[u][s], brec[u][s]) for u in range(5) for s in range(2))
 lp = pb.LodParams.from_buffer_copy(bytes(make_lod_params(levels=6)))
 lq = pb.QpSet.from_buffer_copy(bytes(make_qpset(qp=30, fixed_point_qp_offset=24)))
 vals, lrec, lcp = pb.attr_lift_encode(lp, lq, xyz[:4000], attrs[:4000], lcp_enabled=1)
@@ -34,7 +44,6 @@ print("sanitizer run: results exact")
 PY
 for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   echo "== compute-sanitizer --tool $tool"
-  if [ $tool = racecheck ]; then export PCCB200_HANDOVER=0; else unset PCCB200_HANDOVER; fi
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san.py 2>&1 | tail -8
   echo "exit code: $?"
 done
