@@ -465,6 +465,7 @@ struct DeviceExec {
     a.keep = fn.keep;
     a.nb = alloc<int32_t>(size_t(nCells) * 19);
     a.decPos = alloc<int4>(size_t(nCells));
+    zero(a.decPos, size_t(nCells) * sizeof(int4));
     Scope sc(*this);
     const int64_t threads = int64_t(nCells) * 19;
     k_cell_neighbours<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(a);

@@ -7,11 +7,14 @@
 //   * k_subsample_cells: one warp per cell in Morton ticket order.  A cell's
 //     latency is what bounds a level (cells wait for the decisions of earlier
 //     neighbour cells), so the cell's first points are fetched before the
-//     wait; then 19 lanes poll the decision words of the neighbour cells and
-//     read the retained point's position, which the deciding cell publishes
-//     next to its decision (one dependent access instead of three); the
-//     cell's points are tested one after the other, all neighbours at once
-//     (ballot).
+//     wait; then 19 lanes poll the 16-byte records of the neighbour cells:
+//     (x, y, z, state) of the cell's retained point, written with ONE aligned
+//     16-byte store and read with one 16-byte load (a single transaction
+//     each, as in the status + value words of a decoupled look-back scan), so
+//     that the hop from a cell to the next is one L2 round trip: no release
+//     fence on the producer's side, no second dependent load on the
+//     consumer's; the cell's points are tested one after the other, all
+//     neighbours at once (ballot).
 #pragma once
 
 #include "lod_core.cuh"
@@ -27,8 +30,28 @@ struct SubsampleCellsArgs {
   int* decision;
   uint8_t* keep;
   int32_t* nb;  // nCells * 19 neighbour cell indices (or -1)
-  int4* decPos;  // per cell: position of its retained point (valid once decision >= 0)
+  int4* decPos;  // per cell: (x, y, z) of its retained point, w = kCellRec* (zeroed before the launch)
 };
+
+constexpr int kCellRecUndecided = 0, kCellRecNone = 1, kCellRecPoint = 2;
+
+__device__ __forceinline__ int4
+ld_cell_rec(const int4* p)
+{
+  int4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void
+st_cell_rec(int4* p, int x, int y, int z, int w)
+{
+  asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y),
+               "r"(z), "r"(w)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(256)
 k_cell_neighbours(const SubsampleCellsArgs a)
@@ -89,11 +112,12 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
     bool have = false;
     int32_t np[3] = {0, 0, 0};
     if (q >= 0) {
-      int d;
-      while ((d = ld_acquire(&a.decision[q])) == kCellUndecided)
+      int4 r = ld_cell_rec(&a.decPos[q]);
+      while (r.w == kCellRecUndecided) {
         __nanosleep(32);
-      if (d >= 0) {
-        const int4 r = a.decPos[q];
+        r = ld_cell_rec(&a.decPos[q]);
+      }
+      if (r.w == kCellRecPoint) {
         np[0] = r.x;
         np[1] = r.y;
         np[2] = r.z;
@@ -117,8 +141,7 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
         chosen = i;
         // the retained point's position travels with the decision
         if (lane == 0) {
-          a.decPos[c] = make_int4(pp[0], pp[1], pp[2], 0);
-          st_release(&a.decision[c], chosen);
+          st_cell_rec(&a.decPos[c], pp[0], pp[1], pp[2], kCellRecPoint);
           a.keep[i] = 1;
         }
         for (int r = i + 1 + lane; r < i1; r += 32)
@@ -129,7 +152,7 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
         a.keep[i] = 0;
     }
     if (chosen == kCellNone && lane == 0)
-      st_release(&a.decision[c], kCellNone);
+      st_cell_rec(&a.decPos[c], 0, 0, 0, kCellRecNone);
   }
 }
 
