@@ -447,6 +447,22 @@ int pccb200_attr_lift_decode_slices(const pccb200_lod_params* lod, const pccb200
                                     int32_t num_slices, const int32_t* values_in,
                                     const int8_t* lcp_coeffs);
 
+/* The same with device pointers for point_qp_offsets, xyz, attrs (coded in
+ * place) and values (slice_offsets and the lcp coefficients stay host arrays);
+ * stream-ordering note as for the RAHT *_dev entries. */
+int pccb200_attr_lift_encode_slices_dev(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                        int32_t lcp_enabled, const int32_t* d_point_qp_offsets,
+                                        const int32_t* d_xyz, int32_t* d_attrs_inout,
+                                        int32_t num_attrs, int32_t bitdepth,
+                                        const int64_t* slice_offsets, int32_t num_slices,
+                                        int32_t* d_values_out, int8_t* lcp_coeffs_out);
+int pccb200_attr_lift_decode_slices_dev(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                        int32_t lcp_enabled, const int32_t* d_point_qp_offsets,
+                                        const int32_t* d_xyz, int32_t* d_attrs_out,
+                                        int32_t num_attrs, int32_t bitdepth,
+                                        const int64_t* slice_offsets, int32_t num_slices,
+                                        const int32_t* d_values_in, const int8_t* lcp_coeffs);
+
 /* Levels of detail kept across the attributes of a slice ------------------------
  *
  * AttributeEncoder / AttributeDecoder keep the LoDs of a slice

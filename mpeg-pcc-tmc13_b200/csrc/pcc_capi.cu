@@ -1163,7 +1163,8 @@ pccb200_lift_dequantize(const pccb200_qpset* qpset, const int32_t* point_qp_offs
 static int
 attr_lift_common(bool forward, const pccb200_lod_params* lod, const pccb200_qpset* qpset,
                  int32_t lcpEnabled, const int32_t* qpo, const int32_t* xyz, int32_t* attrs,
-                 int32_t A, int32_t n, int32_t bitdepth, int32_t* values, int8_t* lcp)
+                 int32_t A, int32_t n, int32_t bitdepth, int32_t* values, int8_t* lcp,
+                 bool device = false)
 {
   if (!lod || !qpset || !xyz || !attrs || !values || n <= 0 || (A != 1 && A != 3)
       || bitdepth < 1 || bitdepth > 16)
@@ -1176,20 +1177,26 @@ attr_lift_common(bool forward, const pccb200_lod_params* lod, const pccb200_qpse
       lcpLocal[l] = lcp[l];
   }
   int rc = with_device([&](DeviceExec& ex) -> int {
-    int32_t* dXyz = to_device(ex, xyz, size_t(n) * 3);
-    int32_t* dIn = forward ? to_device(ex, attrs, size_t(n) * A) : nullptr;
-    int32_t* dQpoIn = qpo ? to_device(ex, qpo, size_t(n) * 2) : nullptr;
-    int32_t* dV = forward ? ex.alloc<int32_t>(size_t(n) * A) : to_device(ex, values, size_t(n) * A);
-    int32_t* dOut = ex.alloc<int32_t>(size_t(n) * A);
+    // device: xyz / qpo / attrs / values are device pointers; attrs is coded in
+    // place (the gather reads it before the final write-back overwrites it)
+    const int32_t* dXyz = device ? xyz : to_device(ex, xyz, size_t(n) * 3);
+    const int32_t* dIn = !forward ? nullptr : device ? attrs : to_device(ex, attrs, size_t(n) * A);
+    const int32_t* dQpoIn = !qpo ? nullptr : device ? qpo : to_device(ex, qpo, size_t(n) * 2);
+    int32_t* dV = device ? values
+                         : forward ? ex.alloc<int32_t>(size_t(n) * A)
+                                   : to_device(ex, values, size_t(n) * A);
+    int32_t* dOut = device ? attrs : ex.alloc<int32_t>(size_t(n) * A);
     int rc2 = attr_lift_run(ex, forward, *lod, *qpset, lcpEnabled != 0, dQpoIn, dXyz, dIn, dOut, A,
                             n, bitdepth, dV, lcpLocal);
     if (rc2 != PCCB200_OK)
       return fail(rc2, rc2 == PCCB200_ERR_UNSUPPORTED
                          ? "a predictor references its own level of detail"
                          : "invalid lifting parameters");
-    to_host(ex, attrs, dOut, size_t(n) * A);
-    if (forward)
-      to_host(ex, values, dV, size_t(n) * A);
+    if (!device) {
+      to_host(ex, attrs, dOut, size_t(n) * A);
+      if (forward)
+        to_host(ex, values, dV, size_t(n) * A);
+    }
     return PCCB200_OK;
   });
   if (rc == PCCB200_OK && forward && lcp)
@@ -1409,7 +1416,7 @@ static int
 attr_lift_slices(bool forward, const pccb200_lod_params* lod, const pccb200_qpset* qpset,
                  int32_t lcpEnabled, const int32_t* qpo, const int32_t* xyz, int32_t* attrs,
                  int32_t A, int32_t bitdepth, const int64_t* sliceOffsets, int32_t numSlices,
-                 int32_t* values, int8_t* lcp)
+                 int32_t* values, int8_t* lcp, bool device = false)
 {
   if (!sliceOffsets || numSlices <= 0)
     return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
@@ -1423,7 +1430,7 @@ attr_lift_slices(bool forward, const pccb200_lod_params* lod, const pccb200_qpse
     return attr_lift_common(forward, lod, qpset, lcpEnabled, qpo ? qpo + 2 * o : nullptr,
                             xyz + 3 * o, attrs + o * A, A, int32_t(sliceOffsets[s + 1] - o),
                             bitdepth, values + o * A,
-                            lcp ? lcp + size_t(s) * PCCB200_MAX_LODS : nullptr);
+                            lcp ? lcp + size_t(s) * PCCB200_MAX_LODS : nullptr, device);
   });
 }
 
@@ -1450,6 +1457,33 @@ pccb200_attr_lift_decode_slices(const pccb200_lod_params* lod, const pccb200_qps
   return attr_lift_slices(false, lod, qpset, lcp_enabled, point_qp_offsets, xyz, attrs_out,
                           num_attrs, bitdepth, slice_offsets, num_slices,
                           const_cast<int32_t*>(values_in), const_cast<int8_t*>(lcp_coeffs));
+}
+
+int
+pccb200_attr_lift_encode_slices_dev(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                    int32_t lcp_enabled, const int32_t* d_point_qp_offsets,
+                                    const int32_t* d_xyz, int32_t* d_attrs_inout,
+                                    int32_t num_attrs, int32_t bitdepth,
+                                    const int64_t* slice_offsets, int32_t num_slices,
+                                    int32_t* d_values_out, int8_t* lcp_coeffs_out)
+{
+  return attr_lift_slices(true, lod, qpset, lcp_enabled, d_point_qp_offsets, d_xyz, d_attrs_inout,
+                          num_attrs, bitdepth, slice_offsets, num_slices, d_values_out,
+                          lcp_coeffs_out, true);
+}
+
+int
+pccb200_attr_lift_decode_slices_dev(const pccb200_lod_params* lod, const pccb200_qpset* qpset,
+                                    int32_t lcp_enabled, const int32_t* d_point_qp_offsets,
+                                    const int32_t* d_xyz, int32_t* d_attrs_out, int32_t num_attrs,
+                                    int32_t bitdepth, const int64_t* slice_offsets,
+                                    int32_t num_slices, const int32_t* d_values_in,
+                                    const int8_t* lcp_coeffs)
+{
+  return attr_lift_slices(false, lod, qpset, lcp_enabled, d_point_qp_offsets, d_xyz, d_attrs_out,
+                          num_attrs, bitdepth, slice_offsets, num_slices,
+                          const_cast<int32_t*>(d_values_in), const_cast<int8_t*>(lcp_coeffs),
+                          true);
 }
 
 //----------------------------------------------------------------------------

@@ -79,8 +79,10 @@ PREDICTOR_DTYPE = np.dtype([("neighbor_count", "<u4"), ("predictor_index", "<u4"
 
 EXPORTS = [
     "pccb200_abi_version", "pccb200_attr_lift_decode", "pccb200_attr_lift_decode_lod",
-    "pccb200_attr_lift_decode_slices", "pccb200_attr_lift_encode", "pccb200_attr_lift_encode_lod",
-    "pccb200_attr_lift_encode_slices", "pccb200_attr_raht_decode",
+    "pccb200_attr_lift_decode_slices", "pccb200_attr_lift_decode_slices_dev",
+    "pccb200_attr_lift_encode", "pccb200_attr_lift_encode_lod",
+    "pccb200_attr_lift_encode_slices", "pccb200_attr_lift_encode_slices_dev",
+    "pccb200_attr_raht_decode",
     "pccb200_attr_raht_decode_multi", "pccb200_attr_raht_decode_multi_batch",
     "pccb200_attr_raht_decode_multi_batch_dev", "pccb200_attr_raht_decode_multi_dev",
     "pccb200_attr_raht_decode_slices_dev", "pccb200_attr_raht_encode",
@@ -467,6 +469,20 @@ def attr_lift_encode(lod_params, qpset, xyz, attrs, lcp_enabled=0, bitdepth=8, q
         _p(xyz, C.c_int32), _p(attrs, C.c_int32), C.c_int32(a), C.c_int32(n), C.c_int32(bitdepth),
         _p(values, C.c_int32), _p(lcp, C.c_int8)))
     return values, attrs, lcp[:lod_params.num_detail_levels].copy()
+
+
+def attr_lift_slices_dev(forward, lod_params, qpset, lcp_enabled, d_xyz, d_attrs, a, slice_offsets,
+                         d_values, lcp, bitdepth=8, d_qpoffs=None):
+    """device pointers (ints) for xyz / attrs (coded in place) / values; slice_offsets
+    (host, int64, numSlices + 1); lcp: host int8 [numSlices, MAX_LODS] (out when forward)"""
+    so = np.ascontiguousarray(slice_offsets, dtype=np.int64)
+    ns = len(so) - 1
+    fn = (lib().pccb200_attr_lift_encode_slices_dev if forward
+          else lib().pccb200_attr_lift_decode_slices_dev)
+    _check(fn(C.byref(lod_params), C.byref(qpset), C.c_int32(lcp_enabled),
+              C.c_void_p(d_qpoffs) if d_qpoffs else None, C.c_void_p(d_xyz), C.c_void_p(d_attrs),
+              C.c_int32(a), C.c_int32(bitdepth), _p(so, C.c_int64), C.c_int32(ns),
+              C.c_void_p(d_values), _p(lcp, C.c_int8)))
 
 
 def attr_lift_decode(lod_params, qpset, xyz, values, lcp=None, bitdepth=8, qpoffs=None):

@@ -523,6 +523,36 @@ def test_lifting_end_to_end(b200):
     assert np.array_equal(inv, attrs)
 
 
+def test_lifting_slices_device_pointers(b200):
+    """the device-pointer lifting entries (slices of a frame, coded in place)
+    against the host-pointer single-slice entry, encoder and decoder"""
+    import torch
+
+    xyz, rgb = cloud_shell(90000, bits=9, seed=31)
+    offs = np.array([0, 40000, 90000], dtype=np.int64)
+    lp = b200.LodParams.from_buffer_copy(bytes(make_lod_params(levels=5)))
+    lq = b200.QpSet.from_buffer_copy(bytes(make_qpset(qp=30, fixed_point_qp_offset=24)))
+    dev = torch.device("cuda", 0)
+    dxyz = torch.from_numpy(np.ascontiguousarray(xyz, dtype=np.int32)).to(dev)
+    dattr = torch.from_numpy(np.ascontiguousarray(rgb, dtype=np.int32)).to(dev)
+    dvals = torch.zeros_like(dattr)
+    lcp = np.zeros((2, b200.MAX_LODS), dtype=np.int8)
+    torch.cuda.synchronize()
+    b200.attr_lift_slices_dev(True, lp, lq, 1, dxyz.data_ptr(), dattr.data_ptr(), 3, offs,
+                              dvals.data_ptr(), lcp)
+    rec, vals = dattr.cpu().numpy(), dvals.cpu().numpy()
+    for s in range(2):
+        sl = slice(int(offs[s]), int(offs[s + 1]))
+        v1, r1, l1 = b200.attr_lift_encode(lp, lq, xyz[sl], rgb[sl], lcp_enabled=1)
+        assert np.array_equal(vals[sl], v1) and np.array_equal(rec[sl], r1), s
+        assert np.array_equal(lcp[s, :len(l1)], l1), s
+    dout = torch.zeros_like(dattr)
+    torch.cuda.synchronize()
+    b200.attr_lift_slices_dev(False, lp, lq, 1, dxyz.data_ptr(), dout.data_ptr(), 3, offs,
+                              dvals.data_ptr(), lcp)
+    assert np.array_equal(dout.cpu().numpy(), rec)
+
+
 @pytest.mark.parametrize("a", [1, 3])
 def test_lifting_attribute_coder(b200, a):
     """pccb200_attr_lift_encode / _decode (LoD build, weights, lifting, LCP +
