@@ -750,6 +750,38 @@ def run_extras(args, pb, rank, world, params, qpset, frame, run_jobs):
     except Exception as e:
         out["lifting_path"] = {"error": str(e)[:200]}
 
+    # ---- recolouring: attribute transfer of the frame's colours
+    # onto a half-resolution (duplicate-merged) geometry, host-pointer ABI
+    try:
+        half = np.ascontiguousarray(np.unique(np.rint(xyz * 0.5).astype(np.int32), axis=0))
+        rp = pb.default_recolour_params()
+        pb.recolour(rp, xyz, rgb, half, 0.5)
+        t0 = time.perf_counter()
+        got = pb.recolour(rp, xyz, rgb, half, 0.5)
+        rec_s = time.perf_counter() - t0
+        rec = {"source_points": int(xyz.shape[0]), "target_points": int(half.shape[0]),
+               "ms": 1e3 * rec_s, "mpoints_per_s": xyz.shape[0] / rec_s / 1e6,
+               "note": "RGB, defaults of tmc3/TMC3.cpp:1500-1551 (8 forward / 1 backward "
+                       "neighbours), host-pointer ABI, pageable buffers, wall clock"}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import pcc_testlib as tl
+        if tl.recolourref_available():
+            m = 200000  # bounded CPU sample: the first 200k source points and their targets
+            sx, sa = xyz[:m], rgb[:m]
+            st = np.ascontiguousarray(np.unique(np.rint(sx * 0.5).astype(np.int32), axis=0))
+            t0 = time.perf_counter()
+            ref = tl.ref_recolour(tl.make_recolour_params(), sx, sa, 0.5, (0, 0, 0), st)
+            cpu_s = time.perf_counter() - t0
+            mine = pb.recolour(rp, sx, sa, st, 0.5)
+            rec["cpu_reference"] = {"source_points": m, "seconds_one_core": cpu_s,
+                                    "mpoints_per_s": m / cpu_s / 1e6,
+                                    "identical_points": float((mine == ref).all(axis=1).mean()),
+                                    "mean_abs_diff": float(np.abs(mine - ref).mean())}
+        out["recolouring"] = rec
+        del got
+    except Exception as e:
+        out["recolouring"] = {"error": str(e)[:200]}
+
     # ---- the two rows either side of the transform
     try:
         theta = np.rint(np.tan(np.linspace(-0.43, 0.04, 64)) * (1 << 18)).astype(np.int32)

@@ -299,6 +299,57 @@ int pccb200_attr_raht_decode_multi_batch_dev(const pccb200_raht_params* params, 
                                              const int32_t* num_attrs, const int32_t* bitdepths,
                                              const int32_t* n, const int32_t* const* d_coeffs_in);
 
+/* Recolouring: attribute transfer to the coded geometry ---------------------------
+ *
+ * When geometry coding adds or removes points (duplicate merging, lossy
+ * quantisation, trisoup) the encoder transfers the attributes of the source
+ * cloud onto the points it is going to code, right before attribute coding
+ * (tmc3/encoder.cpp:1031-1037; recolour / recolourColour / recolourReflectance,
+ * tmc3/pointset_processing.cpp:253-958).  For every target point: the
+ * num_neighbours_fwd nearest source points give a (distance-weighted) forward
+ * colour; the source points that have the target among their
+ * num_neighbours_bwd nearest targets give a backward centroid; the result is
+ * the colour within +-search_range of that centroid that minimises the larger
+ * of the two squared errors.  Positions relate by
+ *     posInTgt = posInSrc * source_to_target_scale - tgt_to_src_offset.
+ *
+ * The reference searches with nanoflann kd-trees; here both searches are exact
+ * k-nearest-neighbour queries over a grid hash (see csrc/recolour.cuh), double
+ * precision, the reference's operation order.  Ties in distance are broken by
+ * the lower point index -- nanoflann's choice among equidistant candidates
+ * depends on its tree traversal -- so the result is bit-exact against the
+ * oracle (same rule) and equal to the compiled reference except where a tie
+ * reaches the k-th neighbour (tests/test_recolour.py states the tolerance).
+ * Coordinates must lie in [0, 2^21).  num_attrs is 3 (colour) or 1
+ * (reflectance); attrs are N x num_attrs, row-major.  Fields mirror
+ * RecolourParams (tmc3/pointset_processing.h:47-63); defaults =
+ * tmc3/TMC3.cpp:1500-1551. */
+typedef struct pccb200_recolour_params {
+  double dist_offset_fwd;            /* 4 */
+  double dist_offset_bwd;            /* 4 */
+  double max_geometry_dist2_fwd;     /* 1000 (>= 512: unlimited) */
+  double max_geometry_dist2_bwd;     /* 1000 */
+  double max_attribute_dist2_fwd;    /* 1000 */
+  double max_attribute_dist2_bwd;    /* 1000 */
+  int32_t search_range;              /* 1 */
+  int32_t num_neighbours_fwd;        /* 8 (<= 16) */
+  int32_t num_neighbours_bwd;        /* 1 (<= 16) */
+  int32_t use_dist_weighted_avg_fwd; /* 1 */
+  int32_t use_dist_weighted_avg_bwd; /* 1 */
+  int32_t skip_avg_if_identical_source_point_present_fwd; /* 1 */
+  int32_t skip_avg_if_identical_source_point_present_bwd; /* 0 */
+  int32_t reserved;
+} pccb200_recolour_params;
+
+void pccb200_recolour_params_default(pccb200_recolour_params* p);
+
+/* Host pointers.  target_attrs_out: n_target x num_attrs. */
+int pccb200_recolour(const pccb200_recolour_params* params, const int32_t* source_xyz,
+                     const int32_t* source_attrs, int32_t num_attrs, int32_t n_source,
+                     double source_to_target_scale, const int32_t tgt_to_src_offset[3],
+                     const int32_t* target_xyz, int32_t n_target, int32_t bitdepth,
+                     int32_t* target_attrs_out);
+
 /* Per-phase device timing (CUDA events around every kernel launch on
  * the call's stream).  Phases: 0 Morton keys + radix sort, 1 tree build
  * (histogram, compaction, leaf / merge kernels), 2 block transform (the

@@ -387,6 +387,8 @@ struct DeviceExec {
 
   // Morton keys + stable radix sort (defined in morton_sort.cuh)
   void morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* order);
+  // in-place exclusive prefix sum (defined in morton_sort.cuh)
+  void exclusive_scan(int* data, int64_t n);
 
   template<class F>
   void foreach(int64_t n, const F& f)

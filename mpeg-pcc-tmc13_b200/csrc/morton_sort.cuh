@@ -342,4 +342,20 @@ DeviceExec::morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* o
   device_morton_sort(*this, xyz, n, keys, order);
 }
 
+// in-place exclusive prefix sum of n ints (the scan of the radix sort's histograms)
+inline void
+DeviceExec::exclusive_scan(int* data, int64_t n)
+{
+  if (n <= 0)
+    return;
+  const int scanTiles = int((n + kTile - 1) / kTile);
+  int* tileSums = alloc<int>(scanTiles);
+  Scope sc(*this);
+  k_scan_sum<<<scanTiles, kTileThreads, 0, stream>>>(data, n, tileSums);
+  k_scan_tiles<<<1, 1024, 0, stream>>>(tileSums, scanTiles, nullptr);
+  k_scan_apply<<<scanTiles, kTileThreads, 0, stream>>>(data, n, tileSums);
+  g_launchCount += 3;
+  PCC_CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace pccb200

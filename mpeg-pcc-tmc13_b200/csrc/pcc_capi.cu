@@ -27,6 +27,7 @@
 #include "spherical.cuh"
 #include "symbols.cuh"
 #include "dist2.cuh"
+#include "recolour.cuh"
 
 namespace pccb200 {
 
@@ -1679,6 +1680,56 @@ pccb200_quant_weights_scalable(const uint32_t* num_points_in_lod, int32_t lod_co
     if (rc != PCCB200_OK)
       return fail(rc, "numPointsInLod does not partition [0, n)");
     to_host(ex, qw_out, dQw, size_t(n));
+    return PCCB200_OK;
+  });
+}
+
+//----------------------------------------------------------------------------
+// recolouring (recolour.cuh)
+
+void
+pccb200_recolour_params_default(pccb200_recolour_params* p)
+{
+  if (!p)
+    return;
+  // tmc3/TMC3.cpp:1500-1551
+  p->dist_offset_fwd = 4.;
+  p->dist_offset_bwd = 4.;
+  p->max_geometry_dist2_fwd = 1000.;
+  p->max_geometry_dist2_bwd = 1000.;
+  p->max_attribute_dist2_fwd = 1000.;
+  p->max_attribute_dist2_bwd = 1000.;
+  p->search_range = 1;
+  p->num_neighbours_fwd = 8;
+  p->num_neighbours_bwd = 1;
+  p->use_dist_weighted_avg_fwd = 1;
+  p->use_dist_weighted_avg_bwd = 1;
+  p->skip_avg_if_identical_source_point_present_fwd = 1;
+  p->skip_avg_if_identical_source_point_present_bwd = 0;
+  p->reserved = 0;
+}
+
+int
+pccb200_recolour(const pccb200_recolour_params* params, const int32_t* source_xyz,
+                 const int32_t* source_attrs, int32_t num_attrs, int32_t n_source,
+                 double source_to_target_scale, const int32_t tgt_to_src_offset[3],
+                 const int32_t* target_xyz, int32_t n_target, int32_t bitdepth,
+                 int32_t* target_attrs_out)
+{
+  if (!params || !source_xyz || !source_attrs || !tgt_to_src_offset || !target_xyz
+      || !target_attrs_out || n_source <= 0 || n_target <= 0 || (num_attrs != 1 && num_attrs != 3))
+    return fail(PCCB200_ERR_INVALID_ARG, "null pointer or bad size");
+  return with_device([&](DeviceExec& ex) -> int {
+    int32_t* dSrc = to_device(ex, source_xyz, size_t(n_source) * 3);
+    int32_t* dAttr = to_device(ex, source_attrs, size_t(n_source) * num_attrs);
+    int32_t* dTgt = to_device(ex, target_xyz, size_t(n_target) * 3);
+    int32_t* dOut = ex.alloc<int32_t>(size_t(n_target) * num_attrs);
+    int rc = recolour_run(ex, *params, dSrc, dAttr, num_attrs, n_source, source_to_target_scale,
+                          tgt_to_src_offset, dTgt, n_target, bitdepth, dOut);
+    if (rc != PCCB200_OK)
+      return fail(rc, "invalid recolouring parameters (neighbour counts, scale, or a coordinate "
+                      "outside [0, 2^21))");
+    to_host(ex, target_attrs_out, dOut, size_t(n_target) * num_attrs);
     return PCCB200_OK;
   });
 }

@@ -97,7 +97,8 @@ EXPORTS = [
     "pccb200_offset_and_scale", "pccb200_profile_enable", "pccb200_profile_read",
     "pccb200_profile_reset", "pccb200_quant_weights", "pccb200_quant_weights_fixed",
     "pccb200_quant_weights_scalable", "pccb200_raht_forward", "pccb200_raht_inverse",
-    "pccb200_raht_params_default", "pccb200_raht_set_prediction_weights", "pccb200_set_device",
+    "pccb200_raht_params_default", "pccb200_raht_set_prediction_weights", "pccb200_recolour",
+    "pccb200_recolour_params_default", "pccb200_set_device",
     "pccb200_time_begin", "pccb200_time_end", "pccb200_xyz_to_rpl",
 ]
 NUM_PHASES = 8
@@ -365,6 +366,40 @@ def attr_raht_multi_batch_dev(forward, params, qpsets, d_xyzs, d_attrs, d_coefs,
     fn = (lib().pccb200_attr_raht_encode_multi_batch_dev if forward
           else lib().pccb200_attr_raht_decode_multi_batch_dev)
     _check(fn(C.byref(params), C.c_int32(k), qp, C.c_int32(m), xp, at, na, bd, nn, co))
+
+
+class RecolourParams(C.Structure):
+    _fields_ = [("dist_offset_fwd", C.c_double), ("dist_offset_bwd", C.c_double),
+                ("max_geometry_dist2_fwd", C.c_double), ("max_geometry_dist2_bwd", C.c_double),
+                ("max_attribute_dist2_fwd", C.c_double), ("max_attribute_dist2_bwd", C.c_double),
+                ("search_range", C.c_int32), ("num_neighbours_fwd", C.c_int32),
+                ("num_neighbours_bwd", C.c_int32), ("use_dist_weighted_avg_fwd", C.c_int32),
+                ("use_dist_weighted_avg_bwd", C.c_int32),
+                ("skip_avg_if_identical_source_point_present_fwd", C.c_int32),
+                ("skip_avg_if_identical_source_point_present_bwd", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def default_recolour_params():
+    p = RecolourParams()
+    lib().pccb200_recolour_params_default(C.byref(p))
+    return p
+
+
+def recolour(params, source_xyz, source_attrs, target_xyz, scale=1.0, offset=(0, 0, 0), bitdepth=8):
+    """attribute transfer source -> target (pccb200_recolour); -> [n_target, A] int32"""
+    sx = np.ascontiguousarray(source_xyz, dtype=np.int32)
+    sa = np.ascontiguousarray(source_attrs, dtype=np.int32)
+    tx = np.ascontiguousarray(target_xyz, dtype=np.int32)
+    if sa.ndim == 1:
+        sa = sa[:, None]
+    a = sa.shape[1]
+    out = np.zeros((tx.shape[0], a), dtype=np.int32)
+    off = (C.c_int32 * 3)(*[int(v) for v in offset])
+    _check(lib().pccb200_recolour(C.byref(params), _p(sx, C.c_int32), _p(sa, C.c_int32), C.c_int32(a),
+                                  C.c_int32(sx.shape[0]), C.c_double(scale), off, _p(tx, C.c_int32),
+                                  C.c_int32(tx.shape[0]), C.c_int32(bitdepth), _p(out, C.c_int32)))
+    return out
 
 
 def quant_weights(preds, num_points_in_lod):

@@ -8,6 +8,7 @@
 #include "symbols.cuh"
 #include "dist2.cuh"
 #include "raht_pipeline.cuh"
+#include "recolour.cuh"
 
 extern "C" int
 emu_raht(int forward, const pccb200_raht_params* pp, const pccb200_qpset* qs,
@@ -108,3 +109,14 @@ emu_quant_weights_scalable(const uint32_t* npl, int lodCount, uint64_t numPoints
   return pccb200::run_quant_weights_scalable(ex, npl, lodCount, numPoints, minLog2, n, qw);
 }
 
+
+// recolour.cuh (host build)
+extern "C" int
+emu_recolour(const pccb200_recolour_params* rp, const int32_t* srcXyz, const int32_t* srcAttr, int A,
+             int nSrc, double scale, const int32_t* off, const int32_t* tgtXyz, int nTgt,
+             int bitdepth, int32_t* out)
+{
+  HostExec ex;
+  return pccb200::recolour_run(ex, *rp, srcXyz, srcAttr, A, nSrc, scale, off, tgtXyz, nTgt, bitdepth,
+                               out);
+}

@@ -60,6 +60,15 @@ struct HostExec {
       order[i] = idx[i];
     }
   }
+  void exclusive_scan(int* data, int64_t n)
+  {
+    int acc = 0;
+    for (int64_t i = 0; i < n; i++) {
+      const int v = data[i];
+      data[i] = acc;
+      acc += v;
+    }
+  }
   template<class P, class E>
   void compact(int64_t n, const P& pred, const E& emit, int* total = nullptr)
   {

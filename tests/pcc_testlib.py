@@ -750,3 +750,70 @@ def emu_quant_weights_scalable(npl, num_points, min_log2):
     assert rc == 0
     return qw
 
+
+
+# ---- recolouring (attribute transfer) ---------------------------------------
+
+class RecolourParams(C.Structure):
+    _fields_ = [("dist_offset_fwd", C.c_double), ("dist_offset_bwd", C.c_double),
+                ("max_geometry_dist2_fwd", C.c_double), ("max_geometry_dist2_bwd", C.c_double),
+                ("max_attribute_dist2_fwd", C.c_double), ("max_attribute_dist2_bwd", C.c_double),
+                ("search_range", C.c_int32), ("num_neighbours_fwd", C.c_int32),
+                ("num_neighbours_bwd", C.c_int32), ("use_dist_weighted_avg_fwd", C.c_int32),
+                ("use_dist_weighted_avg_bwd", C.c_int32),
+                ("skip_avg_if_identical_source_point_present_fwd", C.c_int32),
+                ("skip_avg_if_identical_source_point_present_bwd", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def make_recolour_params(**kw):
+    """defaults = tmc3/TMC3.cpp:1500-1551"""
+    p = RecolourParams(4., 4., 1000., 1000., 1000., 1000., 1, 8, 1, 1, 1, 1, 0, 0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _run_recolour(fn, params, sxyz, sattr, scale, off, txyz, bitdepth):
+    sxyz = np.ascontiguousarray(sxyz, dtype=np.int32)
+    sattr = np.ascontiguousarray(sattr, dtype=np.int32)
+    txyz = np.ascontiguousarray(txyz, dtype=np.int32)
+    if sattr.ndim == 1:
+        sattr = sattr[:, None]
+    a = sattr.shape[1]
+    out = np.zeros((txyz.shape[0], a), dtype=np.int32)
+    o = np.ascontiguousarray(off, dtype=np.int32)
+    rc = fn(C.byref(params), _ptr(sxyz, C.c_int32), _ptr(sattr, C.c_int32), C.c_int(a),
+            C.c_int(sxyz.shape[0]), C.c_double(scale), _ptr(o, C.c_int32), _ptr(txyz, C.c_int32),
+            C.c_int(txyz.shape[0]), C.c_int(bitdepth), _ptr(out, C.c_int32))
+    assert rc == 0, rc
+    return out
+
+
+def oracle_recolour(params, sxyz, sattr, scale, off, txyz, bitdepth=8):
+    return _run_recolour(load_oracle().oracle_recolour, params, sxyz, sattr, scale, off, txyz, bitdepth)
+
+
+def emu_recolour(params, sxyz, sattr, scale, off, txyz, bitdepth=8):
+    return _run_recolour(load_emu().emu_recolour, params, sxyz, sattr, scale, off, txyz, bitdepth)
+
+
+_recolourref = None
+
+
+def recolourref_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libtmc13_recolour.so"))
+
+
+def ref_recolour(params, sxyz, sattr, scale, off, txyz, bitdepth=8):
+    global _recolourref
+    if _recolourref is None:
+        _recolourref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libtmc13_recolour.so"))
+    return _run_recolour(_recolourref.ref_recolour, params, sxyz, sattr, scale, off, txyz, bitdepth)
+
+
+def coded_geometry(xyz, scale):
+    """the geometry an encoder with lossy, duplicate-merging geometry coding would
+    code: positions scaled, rounded, made unique (encoder.cpp quantizePositionsUniq)"""
+    q = np.rint(xyz.astype(np.float64) * scale).astype(np.int32)
+    return np.ascontiguousarray(np.unique(q, axis=0))
