@@ -212,6 +212,23 @@ struct LcpSumFn {
     const int32_t m12 = int32_t(uint32_t(k1 * k2));
     const int32_t m11 = int32_t(uint32_t(k1 * k1));
     const int l = lt.lod_of(i);
+#if defined(__CUDA_ARCH__)
+    // a warp whose 32 coefficients belong to one level of detail (nearly all of
+    // them) adds once: the sums are modulo 2^64, so the order does not matter
+    if (__activemask() == 0xffffffffu && __match_any_sync(0xffffffffu, l) == 0xffffffffu) {
+      long long a = m12, b = m11;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomic_add_u64(&sums[2 * l], uint64_t(a));
+        atomic_add_u64(&sums[2 * l + 1], uint64_t(b));
+      }
+      return;
+    }
+#endif
     atomic_add_u64(&sums[2 * l], uint64_t(int64_t(m12)));
     atomic_add_u64(&sums[2 * l + 1], uint64_t(int64_t(m11)));
   }
