@@ -481,7 +481,19 @@ struct DeviceExec {
       cap = 8;
     if (blocks > cap)
       blocks = cap;
-    k_subsample_cells<<<unsigned(blocks), 256, 0, stream>>>(a, ticket);
+    const char* ech = getenv("PCCB200_SUBSAMPLE_CHUNK");  // A/B: 0 = every hop through L2
+    if (!ech || atoi(ech) != 0) {
+      int64_t chunks = (int64_t(nCells) + kCellChunk - 1) / kCellChunk;
+      int64_t ccap = int64_t(numSMs) * 4;  // 4 CTAs of 512 threads per SM
+      if (inFlight > 1)
+        ccap /= 2 * inFlight;
+      if (ccap < 4)
+        ccap = 4;
+      k_subsample_cells_chunked<<<unsigned(chunks > ccap ? ccap : chunks), kCellChunkThreads, 0,
+                                  stream>>>(a, ticket);
+    } else {
+      k_subsample_cells<<<unsigned(blocks), 256, 0, stream>>>(a, ticket);
+    }
     g_launchCount += 2;
     PCC_CUDA_CHECK(cudaGetLastError());
   }
