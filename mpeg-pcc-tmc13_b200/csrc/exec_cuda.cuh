@@ -481,8 +481,12 @@ struct DeviceExec {
       cap = 8;
     if (blocks > cap)
       blocks = cap;
-    const char* ech = getenv("PCCB200_SUBSAMPLE_CHUNK");  // A/B: 0 = every hop through L2
-    if (!ech || atoi(ech) != 0) {
+    // A/B knob (default off): chunks of cells per CTA with the records in shared
+    // memory -- measured 12x SLOWER (235 against 20 ms per 1M-point slice,
+    // profiles/r02_y_subsample_chunked.log): the barrier per chunk and 16 warps
+    // per 256 cells cost far more parallelism than the shorter hop returns
+    const char* ech = getenv("PCCB200_SUBSAMPLE_CHUNK");
+    if (ech && atoi(ech) != 0) {
       int64_t chunks = (int64_t(nCells) + kCellChunk - 1) / kCellChunk;
       int64_t ccap = int64_t(numSMs) * 4;  // 4 CTAs of 512 threads per SM
       if (inFlight > 1)

@@ -156,6 +156,8 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
   }
 }
 
+// EXPERIMENT (PCCB200_SUBSAMPLE_CHUNK=1, off by default, measured 12x slower than
+// k_subsample_cells: see exec_cuda.cuh).
 // The same dataflow with chunks of cells per CTA.  Consecutive cells in Morton
 // order are mostly each other's neighbours, and -- unlike the RAHT blocks --
 // a cell has next to no arithmetic of its own: the hop from a cell to the next
