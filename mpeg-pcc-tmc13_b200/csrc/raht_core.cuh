@@ -149,8 +149,18 @@ struct LevelHistFn {
       return;
     }
     uint64_t x = uint64_t(a ^ b);
-    if (x)
-      atomic_add_i32(&hist[63 - clz64(x)], 1);
+    if (!x)
+      return;
+    const int bin = 63 - clz64(x);
+#if defined(__CUDA_ARCH__)
+    // adjacent keys mostly differ in the same few low bits: one atomic per bin
+    // and warp instead of one per point (a million atomics on ~20 words)
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1)
+      atomicAdd(&hist[bin], __popc(peers));
+#else
+    atomic_add_i32(&hist[bin], 1);
+#endif
   }
 };
 

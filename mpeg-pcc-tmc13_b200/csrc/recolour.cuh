@@ -127,8 +127,19 @@ struct GatherPosFn {
     for (int k = 0; k < 3; k++) {
       const int32_t v = xyz[3 * size_t(o) + k];
       spos[3 * i + k] = v;
+#if defined(__CUDA_ARCH__)
+      // one atomic per warp and bound instead of one per point
+      const unsigned act = __activemask();
+      const int lo = __reduce_min_sync(act, v >> shift);
+      const int hi = __reduce_max_sync(act, v >> shift);
+      if ((threadIdx.x & 31) == __ffs(act) - 1) {
+        atomicMin(&bbox[k], lo);
+        atomicMax(&bbox[3 + k], hi);
+      }
+#else
       atomic_min_i32(&bbox[k], v >> shift);
       atomic_max_i32(&bbox[3 + k], v >> shift);
+#endif
     }
   }
 };
@@ -139,8 +150,16 @@ struct DistinctCodeFn {
   int* count;
   PCC_HD void operator()(int64_t i) const
   {
-    if (i == 0 || code[i] != code[i - 1])
+    const bool head = i == 0 || code[i] != code[i - 1];
+#if defined(__CUDA_ARCH__)
+    const unsigned act = __activemask();
+    const unsigned heads = __ballot_sync(act, head);
+    if (heads && (threadIdx.x & 31) == __ffs(act) - 1)
+      atomicAdd(count, __popc(heads));
+#else
+    if (head)
       atomic_add_i32(count, 1);
+#endif
   }
 };
 
