@@ -528,6 +528,29 @@ def run_ours(args):
             ok = bool(torch.equal(drgb, d0["rgb"]) and torch.equal(drefl, d0["refl"]))
             dec = {"single_frame_ms": min(ts), "mpoints_per_s": n / min(ts) / 1e3,
                    "reproduces_encoder_reconstruction": ok}
+            # all frames of the step through the batch entry (gangs, wavefront order)
+            outs = [(torch.empty_like(d["rgb"]), torch.empty_like(d["refl"])) for d in dv]
+
+            def dec_batch():
+                pb.attr_raht_multi_batch_dev(
+                    False, params, qpsets, [d["xyz"].data_ptr() for d in dv],
+                    [[o[0].data_ptr(), o[1].data_ptr()] for o in outs],
+                    [[d["crgb"].data_ptr(), d["crefl"].data_ptr()] for d in dv], [n] * F, [3, 1])
+
+            dec_batch()
+            torch.cuda.synchronize()
+            tb = []
+            for _ in range(2):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                pb.time_begin()
+                dec_batch()
+                tb.append(pb.time_end())
+            okb = bool(all(torch.equal(o[0], d["rgb"]) and torch.equal(o[1], d["refl"])
+                           for o, d in zip(outs, dv)))
+            dec["batch"] = {"frames": F, "ms_per_step": min(tb), "mpoints_per_s": F * n / min(tb) / 1e3,
+                            "reproduces_encoder_reconstruction": okb}
+            del outs
         except Exception as e:
             dec = {"error": str(e)[:200]}
 

@@ -96,3 +96,31 @@ def test_batch_entry_argument_checks():
         rc = call(good[0], good[1], good[2], [3], [8, 5])
         assert rc != 0 and rc != invalid
         assert b"CUDA" in lib.pccb200_last_error() or b"device" in lib.pccb200_last_error()
+
+
+def test_recolour_entry_argument_checks():
+    """pccb200_recolour refuses nulls and bad component counts before it looks for
+    a device; a well-formed call without a GPU fails loudly (no CPU fallback)"""
+    import torch
+
+    import pcc_attr_b200 as pb
+
+    lib = pb.lib()
+    p = pb.default_recolour_params()
+    assert (p.num_neighbours_fwd, p.num_neighbours_bwd, p.search_range) == (8, 1, 1)
+    assert p.dist_offset_fwd == 4.0 and p.max_geometry_dist2_bwd == 1000.0
+    xyz = np.zeros((16, 3), dtype=np.int32)
+    rgb = np.zeros((16, 3), dtype=np.int32)
+    out = np.zeros((16, 3), dtype=np.int32)
+    off = (C.c_int32 * 3)(0, 0, 0)
+
+    def call(sx, sa, a, tx, o):
+        return lib.pccb200_recolour(C.byref(p), sx, sa, C.c_int32(a), C.c_int32(16), C.c_double(1.0),
+                                    off, tx, C.c_int32(16), C.c_int32(8), o)
+
+    P = lambda x: x.ctypes.data_as(C.POINTER(C.c_int32))
+    assert call(None, P(rgb), 3, P(xyz), P(out)) == 1
+    assert call(P(xyz), P(rgb), 2, P(xyz), P(out)) == 1
+    assert call(P(xyz), P(rgb), 3, P(xyz), None) == 1
+    if not torch.cuda.is_available():
+        assert call(P(xyz), P(rgb), 3, P(xyz), P(out)) not in (0, 1)
