@@ -444,6 +444,9 @@ struct DeviceExec {
     PCC_CUDA_CHECK(cudaGetLastError());
   }
 
+  // cells sorted by dependency level (defined in morton_sort.cuh: needs the radix sort)
+  const int32_t* cell_wave_order(const int32_t* nb, int nCells);
+
   // Distance subsampling over cells in Morton order (see lod_subsample_warp.cuh)
   void subsample_distance(const SubsampleDistanceFn& fn, int nCells)
   {
@@ -468,9 +471,15 @@ struct DeviceExec {
     a.nb = alloc<int32_t>(size_t(nCells) * 19);
     a.decPos = alloc<int4>(size_t(nCells));
     zero(a.decPos, size_t(nCells) * sizeof(int4));
+    a.order = nullptr;
     Scope sc(*this);
     const int64_t threads = int64_t(nCells) * 19;
     k_cell_neighbours<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(a);
+    // wavefront order for the large levels (see k_cell_levels); A/B knob
+    // PCCB200_SUBSAMPLE_WAVE=0: Morton order everywhere
+    const char* ew = getenv("PCCB200_SUBSAMPLE_WAVE");
+    if (nCells >= 4096 && !(ew && atoi(ew) == 0))
+      a.order = cell_wave_order(a.nb, nCells);
     PCC_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream));
     int64_t blocks = (int64_t(nCells) + 7) / 8;
     const int inFlight = activeCalls ? activeCalls->load() : 1;

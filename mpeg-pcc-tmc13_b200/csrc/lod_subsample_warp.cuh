@@ -29,6 +29,7 @@ struct SubsampleCellsArgs {
   int shiftBits0;
   int* decision;
   uint8_t* keep;
+  const int32_t* order;  // wavefront schedule: ticket t runs cell order[t] (null: Morton order)
   int32_t* nb;  // nCells * 19 neighbour cell indices (or -1)
   int4* decPos;  // per cell: (x, y, z) of its retained point, w = kCellRec* (zeroed before the launch)
 };
@@ -91,7 +92,7 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= (unsigned long long)a.nCells)
       return;
-    const int c = int(t);
+    const int c = a.order ? a.order[t] : int(t);
     const int q = lane < 19 ? a.nb[size_t(c) * 19 + lane] : -1;
     const int i0 = a.cellFirst[c], i1 = a.cellFirst[c + 1];
     // the first two points of the cell (the same in every lane), before the wait
@@ -153,6 +154,63 @@ k_subsample_cells(const SubsampleCellsArgs a, unsigned long long* ticket)
     }
     if (chosen == kCellNone && lane == 0)
       st_cell_rec(&a.decPos[c], 0, 0, 0, kCellRecNone);
+  }
+}
+
+// Dependency level of every cell (1 + the highest level among the earlier
+// neighbour cells it waits for): geometry only.  Claimed in Morton order, the
+// cells of a long chain sit in the ticket window while cells that could run
+// wait to be claimed (measured: 4 us per hop on a level of 500k cells whose
+// dependency graph is 2 100 deep, 1 us on small levels); sorted by level
+// (wavefront order) a cell is normally ready when a warp takes it.  One thread
+// per cell, 32 consecutive cells per ticket, the polling loop uniform over the
+// warp (as k_block_levels in raht_wave.cuh).
+__global__ void __launch_bounds__(256)
+k_cell_levels(const int32_t* __restrict__ nb, const int nCells, int* lv, int64_t* key,
+              int32_t* val, unsigned long long* ticket)
+{
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)nCells)
+      return;
+    const int c = int(base) + lane;
+    const bool active = c < nCells;
+    int q[19];
+#pragma unroll
+    for (int i = 0; i < 19; i++)
+      q[i] = active ? nb[size_t(c) * 19 + i] : -1;
+    bool done = !active;
+    while (__any_sync(0xffffffffu, !done)) {
+      bool progress = false;
+      if (!done) {
+        int m = 0;
+        bool ready = true;
+#pragma unroll
+        for (int i = 0; i < 19; i++)
+          if (q[i] >= 0) {
+            int v;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(lv + q[i]) : "memory");
+            if (!v)
+              ready = false;
+            else
+              m = v > m ? v : m;
+          }
+        if (ready) {
+          m++;
+          asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(lv + c), "r"(m) : "memory");
+          key[c] = m;
+          val[c] = c;
+          done = true;
+          progress = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, progress))
+        __nanosleep(40);
+    }
   }
 }
 

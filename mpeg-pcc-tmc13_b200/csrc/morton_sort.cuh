@@ -342,6 +342,27 @@ DeviceExec::morton_sort(const int32_t* xyz, int64_t n, int64_t* keys, int32_t* o
   device_morton_sort(*this, xyz, n, keys, order);
 }
 
+inline const int32_t*
+DeviceExec::cell_wave_order(const int32_t* nb, int nCells)
+{
+  int* lv = alloc<int>(size_t(nCells) + 2);
+  zero(lv, (size_t(nCells) + 2) * sizeof(int));
+  unsigned long long* tk = reinterpret_cast<unsigned long long*>(alloc<int64_t>(1));
+  zero(tk, sizeof(unsigned long long));
+  int64_t* keyA = alloc<int64_t>(size_t(nCells));
+  int64_t* keyB = alloc<int64_t>(size_t(nCells));
+  int32_t* valA = alloc<int32_t>(size_t(nCells));
+  int32_t* valB = alloc<int32_t>(size_t(nCells));
+  int64_t blocks = (int64_t(nCells) + 255) / 256;
+  const int64_t cap = int64_t(numSMs) * 8;
+  k_cell_levels<<<unsigned(blocks > cap ? cap : blocks), 256, 0, stream>>>(nb, nCells, lv, keyA, valA, tk);
+  g_launchCount++;
+  int64_t* kres;
+  int32_t* vres;
+  device_radix_sort_pairs(*this, keyA, valA, keyB, valB, nCells, 3, &kres, &vres);
+  return vres;
+}
+
 // in-place exclusive prefix sum of n ints (the scan of the radix sort's histograms)
 inline void
 DeviceExec::exclusive_scan(int* data, int64_t n)
