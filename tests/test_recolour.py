@@ -158,3 +158,41 @@ def test_gpu_full_size():
     g = pb.recolour(pp, xyz, rgb, tx, 0.5)
     e = emu_recolour(p, xyz, rgb, 0.5, (0, 0, 0), tx)
     assert np.array_equal(g, e)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_kernel_bodies_fuzz(seed):
+    """random parameter sets, scales, offsets and cloud shapes (including
+    isolated far points: queries outside the occupied box, rings that grow, the
+    scan-everything fallback): kernel bodies on the host == oracle, bit-exact"""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(200, 3000))
+    if seed % 3 == 0:
+        sx = np.unique(rng.integers(0, int(rng.integers(8, 3000)), size=(n, 3)).astype(np.int32), axis=0)
+    else:
+        sx, _ = cloud_shell(n, bits=int(rng.integers(5, 10)), seed=seed)
+    if seed % 4 == 1:  # a few outliers far away from everything
+        sx = np.concatenate([sx, rng.integers(100000, 2000000, size=(5, 3)).astype(np.int32)])
+    a = 3 if seed % 2 else 1
+    sa = rng.integers(0, 1 << 8, size=(sx.shape[0], a)).astype(np.int32)
+    scale = float(rng.choice([1.0, 0.5, 0.25, 0.731, 1.37, 2.0]))
+    off = tuple(int(v) for v in rng.integers(0, 7, size=3))
+    tx = coded_geometry(sx, scale) - np.array(off, dtype=np.int32)
+    tx = np.ascontiguousarray(tx[(tx >= 0).all(axis=1) & (tx < (1 << 21)).all(axis=1)])
+    if tx.shape[0] < 20:
+        pytest.skip("degenerate target")
+    kf = int(rng.integers(1, min(16, sx.shape[0]) + 1))
+    kb = int(rng.integers(1, min(4, tx.shape[0]) + 1))
+    p = make_recolour_params(
+        num_neighbours_fwd=kf, num_neighbours_bwd=kb, search_range=int(rng.integers(0, 3)),
+        use_dist_weighted_avg_fwd=int(rng.integers(0, 2)), use_dist_weighted_avg_bwd=int(rng.integers(0, 2)),
+        skip_avg_if_identical_source_point_present_fwd=int(rng.integers(0, 2)),
+        skip_avg_if_identical_source_point_present_bwd=int(rng.integers(0, 2)),
+        max_geometry_dist2_fwd=float(rng.choice([1000., 50., 4.])),
+        max_geometry_dist2_bwd=float(rng.choice([1000., 9., 2.])),
+        max_attribute_dist2_fwd=float(rng.choice([1000., 400., 60.])),
+        max_attribute_dist2_bwd=float(rng.choice([1000., 300.])),
+        dist_offset_fwd=float(rng.choice([4., 1., 0.5])), dist_offset_bwd=float(rng.choice([4., 2.])))
+    o = oracle_recolour(p, sx, sa, scale, off, tx)
+    e = emu_recolour(p, sx, sa, scale, off, tx)
+    assert np.array_equal(e, o), (seed, int((e != o).any(axis=1).sum()))
